@@ -1,0 +1,161 @@
+// common.cuh — shared pieces of libagpu.so (sm_100a only; no CPU fallback anywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/agpu.h"
+
+struct agpu_device {
+  int ordinal;
+  cudaStream_t stream;
+  cudaMemPool_t pool;
+  unsigned long long launches;  // kernels launched through this handle
+  int sm_count;
+};
+
+struct agpu_event {
+  cudaEvent_t ev;
+};
+
+#define AGPU_CUDA(expr)                          \
+  do {                                           \
+    cudaError_t _e = (expr);                     \
+    if (_e != cudaSuccess) return (int)_e;       \
+  } while (0)
+
+#define AGPU_REQUIRE(cond)             \
+  do {                                 \
+    if (!(cond)) return AGPU_EINVAL;   \
+  } while (0)
+
+// Every kernel launch goes through this macro so that agpu_launch_count() is exact.
+#define AGPU_LAUNCH(dev, kernel, grid, block, smem, ...)                       \
+  do {                                                                         \
+    kernel<<<(grid), (block), (smem), (dev)->stream>>>(__VA_ARGS__);           \
+    (dev)->launches++;                                                         \
+  } while (0)
+
+static inline int agpu_finish_launch() {
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kBlock = 256;  // threads per CTA for all streaming kernels
+
+static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Streaming global memory access.  Columns are read once and written once, so loads use the
+// evict-first path (ld.global.cs) and stores st.global.cs: nothing here is worth keeping in
+// L1/L2.  BYTES is the per-lane chunk: 16 (LDG.128), 8 (LDG.64) or 4 (LDG.32); a warp always
+// covers 32 consecutive chunks, i.e. one fully coalesced 512/256/128-byte request.
+// ---------------------------------------------------------------------------------------------
+template <int BYTES> struct Raw;
+template <> struct Raw<16> { using type = uint4; };
+template <> struct Raw<8> { using type = uint2; };
+template <> struct Raw<4> { using type = unsigned int; };
+template <> struct Raw<2> { using type = unsigned short; };
+template <> struct Raw<1> { using type = unsigned char; };
+
+// G elements of T, loaded/stored as one chunk
+template <typename T, int G>
+struct alignas(sizeof(T) * G) Vec {
+  T e[G];
+};
+
+template <typename T, int G>
+__device__ __forceinline__ Vec<T, G> ld_vec(const T* base, size_t granule) {
+  using R = typename Raw<sizeof(T) * G>::type;
+  R r = __ldcs(reinterpret_cast<const R*>(base) + granule);
+  Vec<T, G> v;
+  memcpy(&v, &r, sizeof(v));
+  return v;
+}
+
+template <typename T, int G>
+__device__ __forceinline__ void st_vec(T* base, size_t granule, const Vec<T, G>& v) {
+  using R = typename Raw<sizeof(T) * G>::type;
+  R r;
+  memcpy(&r, &v, sizeof(v));
+  __stcs(reinterpret_cast<R*>(base) + granule, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Validity bitmaps handled inside the value kernel.  A tile of the value kernel covers
+// `tile_words` consecutive 32-row words of every bitmap; the first tile_words/4 threads of the
+// CTA move them as 16-byte vectors (128-byte lines per warp), AND-ing up to four inputs.
+// nin == 0 means "no bitmap work".  NULL inputs were removed on the host (NULL = all valid).
+// ---------------------------------------------------------------------------------------------
+struct BmAnd {
+  const uint32_t* in[4];
+  uint32_t* out;
+  int nin;
+  int vec;  // all pointers 16-byte aligned
+  __device__ __forceinline__ void tile(size_t w0, int tile_words, size_t nwords) const;
+};
+
+__device__ __forceinline__ void bm_and_tile(const BmAnd& bm, size_t w0, int tile_words, size_t nwords) {
+  if (bm.nin == 0) return;
+  for (int q = threadIdx.x; q * 4 < tile_words; q += blockDim.x) {
+    size_t w = w0 + (size_t)q * 4;
+    if (w >= nwords) break;
+    if (bm.vec && w + 4 <= nwords) {
+      uint4 r = __ldcs(reinterpret_cast<const uint4*>(bm.in[0] + w));
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (k < bm.nin) {
+          uint4 s = __ldcs(reinterpret_cast<const uint4*>(bm.in[k] + w));
+          r.x &= s.x; r.y &= s.y; r.z &= s.z; r.w &= s.w;
+        }
+      __stcs(reinterpret_cast<uint4*>(bm.out + w), r);
+    } else {
+      for (int j = 0; j < 4 && w + j < nwords; ++j) {
+        uint32_t r = bm.in[0][w + j];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (k < bm.nin) r &= bm.in[k][w + j];
+        bm.out[w + j] = r;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void BmAnd::tile(size_t w0, int tile_words, size_t nwords) const {
+  bm_and_tile(*this, w0, tile_words, nwords);
+}
+
+// host helper: collect the non-NULL validity inputs
+static inline BmAnd make_bm(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d,
+                            uint32_t* out) {
+  BmAnd bm{};
+  bm.out = out;
+  bm.nin = 0;
+  if (!out) return bm;
+  const uint32_t* ins[4] = {a, b, c, d};
+  bool al = aligned16(out);
+  for (int k = 0; k < 4; ++k)
+    if (ins[k]) {
+      bm.in[bm.nin++] = ins[k];
+      al = al && aligned16(ins[k]);
+    }
+  bm.vec = al ? 1 : 0;
+  return bm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dtype -> C type
+// ---------------------------------------------------------------------------------------------
+static inline size_t agpu_dtype_size(int dtype) {
+  switch (dtype) {
+    case AGPU_I8: case AGPU_U8: return 1;
+    case AGPU_I16: case AGPU_U16: return 2;
+    case AGPU_I32: case AGPU_U32: case AGPU_F32: case AGPU_DATE32: return 4;
+    default: return 0;
+  }
+}
+
+// internal launchers shared between translation units
+int agpu_launch_bitmap_and(agpu_device* dev, const BmAnd& bm, size_t n_bits);

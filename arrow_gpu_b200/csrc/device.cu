@@ -1,0 +1,171 @@
+// device.cu — device handle, stream-ordered buffers, copies, events (replaces the reference's
+// GpuDevice: crates/array/src/gpu_utils/gpu_device.rs).
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+extern "C" int agpu_abi_version(void) { return AGPU_ABI_VERSION; }
+
+extern "C" int agpu_device_count(int* out) {
+  if (!out) return AGPU_EINVAL;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *out = 0;
+    cudaGetLastError();
+    return (int)e;
+  }
+  *out = n;
+  return 0;
+}
+
+extern "C" int agpu_device_create(int ordinal, agpu_device** out) {
+  if (!out) return AGPU_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return AGPU_ENODEVICE;
+  }
+  if (ordinal < 0 || ordinal >= n) return AGPU_ENODEVICE;
+  AGPU_CUDA(cudaSetDevice(ordinal));
+  agpu_device* d = new agpu_device();
+  d->ordinal = ordinal;
+  d->launches = 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete d; return (int)e; }
+  e = cudaDeviceGetDefaultMemPool(&d->pool, ordinal);
+  if (e != cudaSuccess) { cudaStreamDestroy(d->stream); delete d; return (int)e; }
+  // keep freed blocks in the pool: every op allocates a fresh output (like the reference) and
+  // the allocation must not cost a cudaMalloc each time
+  unsigned long long threshold = ~0ull;
+  cudaMemPoolSetAttribute(d->pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, ordinal);
+  *out = d;
+  return 0;
+}
+
+extern "C" int agpu_device_destroy(agpu_device* dev) {
+  if (!dev) return AGPU_EINVAL;
+  cudaSetDevice(dev->ordinal);
+  cudaStreamSynchronize(dev->stream);
+  cudaStreamDestroy(dev->stream);
+  delete dev;
+  return 0;
+}
+
+extern "C" void* agpu_device_stream(agpu_device* dev) { return dev ? (void*)dev->stream : nullptr; }
+extern "C" int agpu_device_ordinal(agpu_device* dev) { return dev ? dev->ordinal : -1; }
+extern "C" uint64_t agpu_launch_count(agpu_device* dev) { return dev ? dev->launches : 0; }
+
+extern "C" const char* agpu_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case AGPU_EUNSUPPORTED: return "operation not supported for this dtype";
+    case AGPU_EINVAL: return "invalid argument";
+    case AGPU_ENODEVICE: return "no CUDA device";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown agpu error";
+}
+
+extern "C" int agpu_alloc(agpu_device* dev, size_t bytes, void** out) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!out) return AGPU_EINVAL;
+  *out = nullptr;
+  if (bytes == 0) bytes = 16;  // keep a distinct non-NULL pointer for empty columns
+  AGPU_CUDA(cudaSetDevice(dev->ordinal));
+  AGPU_CUDA(cudaMallocAsync(out, bytes, dev->stream));
+  return 0;
+}
+
+extern "C" int agpu_free(agpu_device* dev, void* ptr) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!ptr) return 0;
+  AGPU_CUDA(cudaFreeAsync(ptr, dev->stream));
+  return 0;
+}
+
+extern "C" int agpu_h2d(agpu_device* dev, void* dst, const void* src, size_t bytes) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (bytes == 0) return 0;
+  AGPU_REQUIRE(dst && src);
+  AGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, dev->stream));
+  return 0;
+}
+
+extern "C" int agpu_d2h(agpu_device* dev, void* dst, const void* src, size_t bytes) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (bytes) {
+    AGPU_REQUIRE(dst && src);
+    AGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream));
+  }
+  AGPU_CUDA(cudaStreamSynchronize(dev->stream));
+  return 0;
+}
+
+extern "C" int agpu_d2d(agpu_device* dev, void* dst, const void* src, size_t bytes) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (bytes == 0) return 0;
+  AGPU_REQUIRE(dst && src);
+  AGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, dev->stream));
+  return 0;
+}
+
+extern "C" int agpu_memset(agpu_device* dev, void* dst, int byte_value, size_t bytes) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (bytes == 0) return 0;
+  AGPU_REQUIRE(dst);
+  AGPU_CUDA(cudaMemsetAsync(dst, byte_value, bytes, dev->stream));
+  return 0;
+}
+
+extern "C" int agpu_sync(agpu_device* dev) {
+  if (!dev) return AGPU_ENODEVICE;
+  AGPU_CUDA(cudaStreamSynchronize(dev->stream));
+  return 0;
+}
+
+extern "C" int agpu_host_alloc(size_t bytes, void** out) {
+  if (!out) return AGPU_EINVAL;
+  AGPU_CUDA(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+  return 0;
+}
+
+extern "C" int agpu_host_free(void* ptr) {
+  if (!ptr) return 0;
+  AGPU_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+
+extern "C" int agpu_event_create(agpu_event** out) {
+  if (!out) return AGPU_EINVAL;
+  agpu_event* e = new agpu_event();
+  cudaError_t err = cudaEventCreate(&e->ev);
+  if (err != cudaSuccess) { delete e; return (int)err; }
+  *out = e;
+  return 0;
+}
+
+extern "C" int agpu_event_destroy(agpu_event* ev) {
+  if (!ev) return 0;
+  cudaEventDestroy(ev->ev);
+  delete ev;
+  return 0;
+}
+
+extern "C" int agpu_event_record(agpu_device* dev, agpu_event* ev) {
+  if (!dev) return AGPU_ENODEVICE;
+  AGPU_REQUIRE(ev);
+  AGPU_CUDA(cudaEventRecord(ev->ev, dev->stream));
+  return 0;
+}
+
+extern "C" int agpu_event_elapsed_ms(agpu_event* start, agpu_event* stop, float* ms) {
+  AGPU_REQUIRE(start && stop && ms);
+  AGPU_CUDA(cudaEventSynchronize(stop->ev));
+  AGPU_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+  return 0;
+}

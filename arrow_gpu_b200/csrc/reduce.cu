@@ -1,0 +1,173 @@
+// reduce.cu — the "next" rows of SURVEY.md §8f: broadcast, sum, any, all.
+#include "elementwise.cuh"
+
+namespace {
+
+// ---- broadcast: array/compute_shaders/{f32,i32,u32}/broadcast.wgsl:9-13 ----
+template <typename U>
+struct BroadcastOp {
+  static constexpr int G = 16 / sizeof(U);
+  U* out;
+  U value;
+  struct In {};
+  __device__ __forceinline__ In load(size_t) const { return In{}; }
+  __device__ __forceinline__ void run(size_t g, const In&) const {
+    Vec<U, G> o;
+#pragma unroll
+    for (int k = 0; k < G; ++k) o.e[k] = value;
+    st_vec<U, G>(out, g, o);
+  }
+  __device__ __forceinline__ void tail(size_t i) const { out[i] = value; }
+};
+
+// ---- sum: arithmetic/compute_shaders/{f32,i32,u32}/aggregate.wgsl:13-42 ----
+// The reference reduces every 256-element workgroup with the pairwise tree
+//   s = 1,2,4..128: x[2*s*k] += x[2*s*k + s]
+// and repeats the pass on the partials (aggregate_kernels.rs:24-52).  f32 addition is not
+// associative, so the same tree is rebuilt here: one warp owns one 256-element group; lane l
+// holds elements 4l..4l+3 of each 128-element half (two coalesced 16-byte loads), sums them as
+// (e0+e1)+(e2+e3) (levels s=1,2), a 5-step xor-butterfly adds lanes l and l^1, l^2 .. l^16
+// (levels s=4..64; a+b == b+a bit-for-bit, so every lane ends with the group's half sum) and
+// the two halves are added last (s=128).  Lanes past the end contribute 0 like the shader's
+// bounds check.
+template <typename T>
+__device__ __forceinline__ T half_sum(const T* __restrict__ in, size_t base, size_t len, int lane) {
+  const size_t i = base + (size_t)lane * 4;
+  T e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+  if (i + 3 < len && ((reinterpret_cast<uintptr_t>(in + i) & 15u) == 0)) {
+    const Vec<T, 4> v = ld_vec<T, 4>(in + i, 0);
+    e0 = v.e[0]; e1 = v.e[1]; e2 = v.e[2]; e3 = v.e[3];
+  } else {
+    if (i < len) e0 = in[i];
+    if (i + 1 < len) e1 = in[i + 1];
+    if (i + 2 < len) e2 = in[i + 2];
+    if (i + 3 < len) e3 = in[i + 3];
+  }
+  T s = (e0 + e1) + (e2 + e3);
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) s = s + __shfl_xor_sync(0xFFFFFFFFu, s, off);
+  return s;
+}
+
+template <typename T, int GROUPS_PER_WARP>
+__global__ void __launch_bounds__(kBlock) sum_pass_kernel(const T* __restrict__ in, const size_t len,
+                                                          T* __restrict__ out, const size_t groups) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (size_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  const size_t g0 = warp * GROUPS_PER_WARP;
+  T r[GROUPS_PER_WARP];
+#pragma unroll
+  for (int k = 0; k < GROUPS_PER_WARP; ++k) {
+    const size_t g = g0 + k;
+    if (g < groups) {
+      const T lo = half_sum<T>(in, g * 256, len, lane);
+      const T hi = half_sum<T>(in, g * 256 + 128, len, lane);
+      r[k] = lo + hi;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < GROUPS_PER_WARP; ++k)
+      if (g0 + k < groups) out[g0 + k] = r[k];
+  }
+}
+
+template <typename T>
+int run_sum(agpu_device* dev, const T* a, size_t n, T* out_dev) {
+  if (n == 0) {
+    AGPU_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(T), dev->stream));
+    return 0;
+  }
+  constexpr int GPW = 4;
+  size_t len = n;
+  const T* in = a;
+  // ping-pong scratch for the partials of each pass
+  const size_t cap = ceil_div(n, (size_t)256);
+  T* buf[2] = {nullptr, nullptr};
+  if (cap > 1) {
+    AGPU_CUDA(cudaMallocAsync((void**)&buf[0], cap * sizeof(T), dev->stream));
+    AGPU_CUDA(cudaMallocAsync((void**)&buf[1], ceil_div(cap, (size_t)256) * sizeof(T), dev->stream));
+  }
+  int which = 0, rc = 0;
+  while (true) {
+    const size_t groups = ceil_div(len, (size_t)256);
+    T* dst = groups == 1 ? out_dev : buf[which];
+    const size_t warps = ceil_div(groups, (size_t)GPW);
+    const size_t grid = ceil_div(warps, (size_t)(kBlock / 32));
+    AGPU_LAUNCH(dev, (sum_pass_kernel<T, GPW>), (unsigned)grid, kBlock, 0, in, len, dst, groups);
+    rc = agpu_finish_launch();
+    if (rc || groups == 1) break;
+    in = dst;
+    len = groups;
+    which ^= 1;
+  }
+  if (buf[0]) cudaFreeAsync(buf[0], dev->stream);
+  if (buf[1]) cudaFreeAsync(buf[1], dev->stream);
+  return rc;
+}
+
+// ---- any / all: logical/compute_shaders/u32/any.wgsl, countbitones.wgsl + Sum ----
+// mode 0 (any): flag when a word has a set bit; mode 1 (all): flag when a word has a clear bit
+// among the first n_bits.  `all` is finished by flipping the flag.
+__global__ void __launch_bounds__(kBlock) bits_find_kernel(const uint32_t* __restrict__ bits, const size_t nwords,
+                                                           const size_t n_bits, const int mode,
+                                                           uint32_t* __restrict__ flag) {
+  const uint32_t tail_mask = (n_bits & 31) ? ((1u << (n_bits & 31)) - 1u) : 0xFFFFFFFFu;
+  uint32_t found = 0;
+  for (size_t w = (size_t)blockIdx.x * kBlock + threadIdx.x; w < nwords; w += (size_t)gridDim.x * kBlock) {
+    uint32_t x = __ldcs(bits + w);
+    const uint32_t m = (w == nwords - 1) ? tail_mask : 0xFFFFFFFFu;
+    x = mode == 0 ? (x & m) : (~x & m);
+    found |= x;
+  }
+  found = __reduce_or_sync(0xFFFFFFFFu, found);
+  if ((threadIdx.x & 31) == 0 && found) atomicOr(flag, 1u);
+}
+
+__global__ void flip_flag_kernel(uint32_t* flag) { *flag = *flag ? 0u : 1u; }
+
+}  // namespace
+
+extern "C" int agpu_broadcast(agpu_device* dev, int dtype, const void* scalar_host, void* out, size_t n) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!scalar_host || (n && !out)) return AGPU_EINVAL;
+  BmAnd none{};
+  switch (agpu_dtype_size(dtype)) {
+    case 4: { BroadcastOp<uint32_t> op{(uint32_t*)out, *(const uint32_t*)scalar_host}; return launch_ew(dev, op, n, none, aligned16(out)); }
+    case 2: { BroadcastOp<uint16_t> op{(uint16_t*)out, *(const uint16_t*)scalar_host}; return launch_ew(dev, op, n, none, aligned16(out)); }
+    case 1: { BroadcastOp<uint8_t> op{(uint8_t*)out, *(const uint8_t*)scalar_host}; return launch_ew(dev, op, n, none, aligned16(out)); }
+    default: return AGPU_EUNSUPPORTED;
+  }
+}
+
+extern "C" int agpu_sum(agpu_device* dev, int dtype, const void* a, size_t n, void* out_dev) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!out_dev || (n && !a)) return AGPU_EINVAL;
+  switch (dtype) {
+    case AGPU_F32: return run_sum<float>(dev, (const float*)a, n, (float*)out_dev);
+    case AGPU_I32: case AGPU_U32: return run_sum<uint32_t>(dev, (const uint32_t*)a, n, (uint32_t*)out_dev);
+    default: return AGPU_EUNSUPPORTED;
+  }
+}
+
+static int find_bits(agpu_device* dev, const uint32_t* bits, size_t n_bits, int mode, uint32_t* result_dev) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!result_dev || (n_bits && !bits)) return AGPU_EINVAL;
+  AGPU_CUDA(cudaMemsetAsync(result_dev, 0, 4, dev->stream));
+  const size_t nwords = (n_bits + 31) / 32;
+  if (nwords) {
+    size_t grid = ceil_div(nwords, (size_t)kBlock);
+    const size_t cap = (size_t)dev->sm_count * 16;
+    if (grid > cap) grid = cap;
+    AGPU_LAUNCH(dev, bits_find_kernel, (unsigned)grid, kBlock, 0, bits, nwords, n_bits, mode, result_dev);
+  }
+  if (mode == 1) AGPU_LAUNCH(dev, flip_flag_kernel, 1, 1, 0, result_dev);
+  return agpu_finish_launch();
+}
+
+extern "C" int agpu_any(agpu_device* dev, const uint32_t* bits, size_t n_bits, uint32_t* result_dev) {
+  return find_bits(dev, bits, n_bits, 0, result_dev);
+}
+extern "C" int agpu_all(agpu_device* dev, const uint32_t* bits, size_t n_bits, uint32_t* result_dev) {
+  return find_bits(dev, bits, n_bits, 1, result_dev);
+}

@@ -1,0 +1,487 @@
+// routines.cu — merge (mask select), take (gather), put (scatter) and filter (compaction):
+// crates/routines.  merge/take/put follow the reference shaders; filter is new surface
+//  built from warp-level prefix sums with shared-memory staging.
+#include "bits.cuh"
+#include "elementwise.cuh"
+
+namespace {
+
+// ============================================================================================
+// merge: routines/compute_shaders/{32bit,16bit,8bit,bool}/merge.wgsl; validity merge.rs:17-86
+// ============================================================================================
+// vout = ((va & m) | (vb & ~m)) & vmask, missing bitmap = all ones (Q7) — one pass over the
+// same tile instead of the reference's up to four dispatches.
+struct BmMerge {
+  const uint32_t *va, *vb, *mask, *vmask;
+  uint32_t* out;
+  int vec;
+  __device__ __forceinline__ uint32_t word(size_t w) const {
+    const uint32_t m = mask[w];
+    const uint32_t a = va ? va[w] : 0xFFFFFFFFu;
+    const uint32_t b = vb ? vb[w] : 0xFFFFFFFFu;
+    const uint32_t vm = vmask ? vmask[w] : 0xFFFFFFFFu;
+    return ((a & m) | (b & ~m)) & vm;
+  }
+  __device__ __forceinline__ void tile(size_t w0, int tile_words, size_t nwords) const {
+    if (!out) return;
+    for (int q = threadIdx.x; q < tile_words; q += blockDim.x) {
+      const size_t w = w0 + q;
+      if (w < nwords) out[w] = word(w);
+    }
+  }
+};
+
+template <typename U>  // U = unsigned type of the element width (select is type-agnostic)
+struct MergeOp {
+  static constexpr int G = 16 / sizeof(U);
+  const U* a;
+  const U* b;
+  const uint32_t* mask;
+  U* out;
+  struct In { Vec<U, G> a, b; uint32_t m; };
+  __device__ __forceinline__ In load(size_t g) const {
+    const size_t bit = g * G;  // G divides 32: a granule's mask bits never straddle a word
+    return In{ld_vec<U, G>(a, g), ld_vec<U, G>(b, g), __ldg(mask + (bit >> 5)) >> (bit & 31)};
+  }
+  __device__ __forceinline__ void run(size_t g, const In& in) const {
+    Vec<U, G> o;
+#pragma unroll
+    for (int k = 0; k < G; ++k) o.e[k] = (in.m >> k) & 1u ? in.a.e[k] : in.b.e[k];
+    st_vec<U, G>(out, g, o);
+  }
+  __device__ __forceinline__ void tail(size_t i) const {
+    out[i] = (mask[i >> 5] >> (i & 31)) & 1u ? a[i] : b[i];
+  }
+};
+
+// bool merge: data and validity are both bitmaps over the same words
+struct BoolMergeOp {
+  const uint32_t *a, *b, *mask;
+  uint32_t* out;
+  BmMerge v;
+  size_t last_word;
+  uint32_t last_mask;
+};
+
+__global__ void __launch_bounds__(kBlock) bool_merge_kernel(const BoolMergeOp op, const size_t nwords) {
+  const size_t w = (size_t)blockIdx.x * kBlock + threadIdx.x;
+  if (w >= nwords) return;
+  const uint32_t m = op.mask[w];
+  uint32_t r = (op.a[w] & m) | (op.b[w] & ~m);
+  uint32_t vr = op.v.out ? op.v.word(w) : 0u;
+  if (w == op.last_word) { r &= op.last_mask; vr &= op.last_mask; }
+  op.out[w] = r;
+  if (op.v.out) op.v.out[w] = vr;
+}
+
+template <typename U>
+int run_merge(agpu_device* dev, const void* a, const void* b, const uint32_t* mask, void* out, size_t n,
+              const BmMerge& bm) {
+  MergeOp<U> op{(const U*)a, (const U*)b, mask, (U*)out};
+  return launch_ew<MergeOp<U>, 4, BmMerge>(dev, op, n, bm, aligned16(a) && aligned16(b) && aligned16(out));
+}
+
+// ============================================================================================
+// take: routines/compute_shaders/32bit/take.wgsl:13-17, bool/take.wgsl:13-33
+// ============================================================================================
+// granule = 4 output rows: one 16-byte chunk of indices per lane, 4 gathers, one chunk store.
+template <typename U>
+struct TakeOp {
+  static constexpr int G = 4;
+  const U* src;
+  size_t src_len;
+  const uint32_t* idx;
+  U* out;
+  struct In { Vec<uint32_t, 4> i; };
+  __device__ __forceinline__ U fetch(uint32_t i) const { return i < src_len ? __ldg(src + i) : (U)0; }
+  __device__ __forceinline__ In load(size_t g) const { return In{ld_vec<uint32_t, 4>(idx, g)}; }
+  __device__ __forceinline__ void run(size_t g, const In& in) const {
+    Vec<U, 4> o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.e[k] = fetch(in.i.e[k]);
+    st_vec<U, 4>(out, g, o);
+  }
+  __device__ __forceinline__ void tail(size_t j) const { out[j] = fetch(idx[j]); }
+};
+
+// bit gather (bool data, or validity alone): bit j of out = bit idx[j] of src
+struct TakeBitsOp {
+  static constexpr int G = 4;
+  const uint32_t* src;
+  size_t src_len;
+  const uint32_t* idx;
+  struct In { Vec<uint32_t, 4> i; };
+  __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
+    return i < src_len ? (__ldg(src + (i >> 5)) >> (i & 31)) & 1u : 0u;
+  }
+  __device__ __forceinline__ In load(size_t g) const { return In{ld_vec<uint32_t, 4>(idx, g)}; }
+  __device__ __forceinline__ uint32_t bits(size_t, const In& in) const {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m |= fetch(in.i.e[k]) << k;
+    return m;
+  }
+  __device__ __forceinline__ bool bit_at(size_t j) const { return fetch(idx[j]); }
+};
+
+// values and their validity bits in one pass over the indices
+template <typename U>
+struct TakeWithValidityOp {
+  static constexpr int G = 4;
+  TakeOp<U> val;
+  TakeBitsOp bit;
+  using In = typename TakeOp<U>::In;
+  __device__ __forceinline__ In load(size_t g) const { return val.load(g); }
+  __device__ __forceinline__ uint32_t bits(size_t g, const In& in) const {
+    val.run(g, in);
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m |= bit.fetch(in.i.e[k]) << k;
+    return m;
+  }
+  __device__ __forceinline__ bool bit_at(size_t j) const {
+    val.tail(j);
+    return bit.fetch(bit.idx[j]);
+  }
+};
+
+template <typename U>
+int run_take(agpu_device* dev, const void* src, size_t src_len, const uint32_t* idx, void* out, size_t m,
+             const uint32_t* vsrc, uint32_t* vout) {
+  const bool al = aligned16(idx) && aligned16(out);
+  TakeOp<U> val{(const U*)src, src_len, idx, (U*)out};
+  BmAnd none{};
+  if (vsrc && vout) {
+    TakeWithValidityOp<U> op{val, TakeBitsOp{vsrc, src_len, idx}};
+    return launch_bits(dev, op, vout, m, none, al);
+  }
+  return launch_ew(dev, val, m, none, al);
+}
+
+// ============================================================================================
+// put: routines/compute_shaders/32bit/put.wgsl:17-23, bool/put.wgsl:17-34
+// ============================================================================================
+template <typename U>
+__global__ void __launch_bounds__(kBlock) put_kernel(const U* __restrict__ src, const uint32_t* __restrict__ si,
+                                                     U* dst, const uint32_t* __restrict__ di, const size_t m) {
+  const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < m) dst[di[i]] = src[si[i]];
+}
+
+__global__ void __launch_bounds__(kBlock) put_bits_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ si,
+                                                          uint32_t* dst, const uint32_t* __restrict__ di, const size_t m) {
+  const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= m) return;  // (the reference lacks this bound: Q9)
+  const uint32_t s = si[i], d = di[i];
+  const uint32_t bit = (src[s >> 5] >> (s & 31)) & 1u;
+  if (bit) atomicOr(dst + (d >> 5), 1u << (d & 31));
+  else atomicAnd(dst + (d >> 5), ~(1u << (d & 31)));
+}
+
+// ============================================================================================
+// filter (compaction)
+// ============================================================================================
+// Tile = 4096 rows = 128 mask words.  Pass 1 (count): one warp per tile, each lane popcounts a
+// 16-byte chunk of (mask & vmask); tile counts go to scratch, the grand total to *total.
+// Pass 2 (scan): exclusive scan of the tile counts -> 64-bit output offsets.
+// Pass 3 (scatter): one CTA per tile.  Warp 0 scans the popcounts of the tile's 128 selection
+// words with shuffles; every thread then loads its rows as coalesced 16-byte granules, finds a
+// selected row's slot as  word_prefix + popc(selection bits below it)  and drops the value into a
+// shared-memory stage, which the CTA finally streams out as contiguous stores.
+constexpr int kFilterTileRows = 4096;
+constexpr int kFilterTileWords = kFilterTileRows / 32;
+
+struct FilterScratch {
+  uint32_t* counts;   // [tiles]
+  uint64_t* offsets;  // [tiles]
+};
+
+inline size_t filter_tiles(size_t n) { return ceil_div(n, (size_t)kFilterTileRows); }
+inline FilterScratch filter_scratch(void* p, size_t n) {
+  const size_t tiles = filter_tiles(n);
+  FilterScratch s;
+  s.offsets = (uint64_t*)p;
+  s.counts = (uint32_t*)((char*)p + ((tiles * 8 + 15) / 16) * 16);
+  return s;
+}
+
+__device__ __forceinline__ uint32_t sel_word(const uint32_t* mask, const uint32_t* vmask, size_t w, size_t nwords,
+                                             size_t n) {
+  if (w >= nwords) return 0u;
+  uint32_t s = mask[w];
+  if (vmask) s &= vmask[w];
+  if (w == nwords - 1 && (n & 31)) s &= (1u << (n & 31)) - 1u;
+  return s;
+}
+
+__global__ void __launch_bounds__(kBlock) filter_count_kernel(const uint32_t* __restrict__ mask,
+                                                              const uint32_t* __restrict__ vmask, const size_t n,
+                                                              uint32_t* __restrict__ counts,
+                                                              unsigned long long* __restrict__ total) {
+  const size_t nwords = (n + 31) / 32;
+  const size_t tiles = (n + kFilterTileRows - 1) / kFilterTileRows;
+  const size_t tile = (size_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  if (tile >= tiles) return;
+  const int lane = threadIdx.x & 31;
+  const size_t w0 = tile * kFilterTileWords + (size_t)lane * 4;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c += __popc(sel_word(mask, vmask, w0 + k, nwords, n));
+#pragma unroll
+  for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, off);
+  if (lane == 0) {
+    counts[tile] = c;
+    if (c) atomicAdd(total, (unsigned long long)c);
+  }
+}
+
+// single-CTA exclusive scan, 8 tiles per thread per round
+__global__ void __launch_bounds__(1024) filter_scan_kernel(const uint32_t* __restrict__ counts,
+                                                           uint64_t* __restrict__ offsets, const size_t tiles) {
+  __shared__ uint64_t warp_tot[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t base = 0; base < tiles; base += 1024 * 8) {
+    const size_t t0 = base + (size_t)threadIdx.x * 8;
+    uint32_t c[8];
+    uint64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      c[k] = t0 + k < tiles ? counts[t0 + k] : 0u;
+      sum += c[k];
+    }
+    uint64_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint64_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t w = warp_tot[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint64_t v = __shfl_up_sync(0xFFFFFFFFu, w, off);
+        if (lane >= off) w += v;
+      }
+      warp_tot[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint64_t carry = carry_s;
+    uint64_t excl = carry + (incl - sum) + (warp ? warp_tot[warp - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (t0 + k < tiles) offsets[t0 + k] = excl;
+      excl += c[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+}
+
+template <typename U, bool HAS_V>
+__global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restrict__ src,
+                                                                const uint32_t* __restrict__ vsrc,
+                                                                const uint32_t* __restrict__ mask,
+                                                                const uint32_t* __restrict__ vmask, const size_t n,
+                                                                const uint32_t* __restrict__ counts,
+                                                                const uint64_t* __restrict__ offsets,
+                                                                U* __restrict__ out, uint32_t* vout) {
+  constexpr int G = 16 / sizeof(U);                   // rows per 16-byte granule
+  constexpr int GPT = kFilterTileRows / G / kBlock;    // granules per thread
+  __shared__ U stage[kFilterTileRows];
+  __shared__ uint32_t sel[kFilterTileWords];
+  __shared__ uint32_t pre[kFilterTileWords];
+  __shared__ uint32_t vstage[HAS_V ? kFilterTileWords : 1];
+
+  const size_t tile = blockIdx.x;
+  const uint32_t count = counts[tile];
+  if (count == 0) return;  // uniform for the CTA
+  const size_t nwords = (n + 31) / 32;
+  const size_t w0 = tile * kFilterTileWords;
+  const size_t row0 = tile * kFilterTileRows;
+
+  if (threadIdx.x < kFilterTileWords) {
+    sel[threadIdx.x] = sel_word(mask, vmask, w0 + threadIdx.x, nwords, n);
+    if (HAS_V) vstage[threadIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {  // exclusive prefix of the 128 popcounts: 4 words per lane
+    const int l = threadIdx.x;
+    uint32_t c[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c[k] = __popc(sel[l * 4 + k]); s += c[k]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (l >= off) incl += v;
+    }
+    uint32_t e = incl - s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { pre[l * 4 + k] = e; e += c[k]; }
+  }
+  __syncthreads();
+
+  const bool full = row0 + kFilterTileRows <= n;
+  Vec<U, G> v[GPT];
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < GPT; ++j) v[j] = ld_vec<U, G>(src + row0, (size_t)j * kBlock + threadIdx.x);
+  }
+#pragma unroll
+  for (int j = 0; j < GPT; ++j) {
+    const int r = (j * kBlock + threadIdx.x) * G;  // first row of the granule within the tile
+    const uint32_t sw = sel[r >> 5];
+    const uint32_t bits = (sw >> (r & 31)) & ((G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u));
+    if (bits == 0) continue;
+    uint32_t pos = pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
+    uint32_t vw = 0;
+    if (HAS_V) vw = vsrc[(row0 + r) >> 5] >> (r & 31);
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      if ((bits >> k) & 1u) {
+        stage[pos] = full ? v[j].e[k] : src[row0 + r + k];
+        if (HAS_V && ((vw >> k) & 1u)) atomicOr(&vstage[pos >> 5], 1u << (pos & 31));
+        ++pos;
+      }
+    }
+  }
+  __syncthreads();
+
+  const uint64_t off = offsets[tile];
+  for (uint32_t i = threadIdx.x; i < count; i += kBlock) out[off + i] = stage[i];
+  if (HAS_V) {
+    const uint32_t lw_n = (count + 31) / 32;
+    const uint32_t s = (uint32_t)(off & 31);
+    if (threadIdx.x < lw_n) {
+      const uint32_t val = vstage[threadIdx.x];
+      const uint64_t gw = (off >> 5) + threadIdx.x;
+      if (val << s) atomicOr(vout + gw, val << s);
+      if (s && (val >> (32 - s))) atomicOr(vout + gw + 1, val >> (32 - s));
+    }
+  }
+}
+
+template <typename U>
+int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const uint32_t* mask, const uint32_t* vmask,
+               size_t n, const FilterScratch& sc, void* out, uint32_t* vout) {
+  const size_t tiles = filter_tiles(n);
+  if (tiles > 0x7FFFFFFFull) return AGPU_EINVAL;
+  if (!aligned16(src)) return AGPU_EINVAL;  // tile bases must be 16-byte aligned
+  if (vsrc && vout) {
+    AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
+    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true>), (unsigned)tiles, kBlock, 0, (const U*)src, vsrc, mask, vmask,
+                n, sc.counts, sc.offsets, (U*)out, vout);
+  } else {
+    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false>), (unsigned)tiles, kBlock, 0, (const U*)src, vsrc, mask, vmask,
+                n, sc.counts, sc.offsets, (U*)out, vout);
+  }
+  return agpu_finish_launch();
+}
+
+}  // namespace
+
+extern "C" int agpu_merge(agpu_device* dev, int dtype, const void* a, const void* b, const uint32_t* mask,
+                          void* out, size_t n, const uint32_t* va, const uint32_t* vb, const uint32_t* vmask,
+                          uint32_t* vout) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (n && (!a || !b || !mask || !out)) return AGPU_EINVAL;
+  if (vout && !va && !vb && !vmask) return AGPU_EINVAL;
+  if (n == 0) return 0;
+  BmMerge bm{va, vb, mask, vmask, vout, 0};
+  if (dtype == AGPU_BOOL) {
+    const size_t nwords = (n + 31) / 32;
+    BoolMergeOp op{(const uint32_t*)a, (const uint32_t*)b, mask, (uint32_t*)out, bm, nwords - 1,
+                   (n & 31) ? ((1u << (n & 31)) - 1u) : 0xFFFFFFFFu};
+    AGPU_LAUNCH(dev, bool_merge_kernel, (unsigned)ceil_div(nwords, (size_t)kBlock), kBlock, 0, op, nwords);
+    return agpu_finish_launch();
+  }
+  switch (agpu_dtype_size(dtype)) {
+    case 4: return run_merge<uint32_t>(dev, a, b, mask, out, n, bm);
+    case 2: return run_merge<uint16_t>(dev, a, b, mask, out, n, bm);
+    case 1: return run_merge<uint8_t>(dev, a, b, mask, out, n, bm);
+    default: return AGPU_EUNSUPPORTED;
+  }
+}
+
+extern "C" int agpu_take(agpu_device* dev, int dtype, const void* src, size_t src_len, const uint32_t* idx,
+                         void* out, size_t m, const uint32_t* vsrc, uint32_t* vout) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (m && (!src || !idx || !out)) return AGPU_EINVAL;
+  if (vout && !vsrc) return AGPU_EINVAL;
+  if (m == 0) return 0;
+  BmAnd none{};
+  if (dtype == AGPU_BOOL) {
+    int rc = launch_bits(dev, TakeBitsOp{(const uint32_t*)src, src_len, idx}, (uint32_t*)out, m, none, aligned16(idx));
+    if (rc || !(vsrc && vout)) return rc;
+    return launch_bits(dev, TakeBitsOp{vsrc, src_len, idx}, vout, m, none, aligned16(idx));
+  }
+  switch (agpu_dtype_size(dtype)) {
+    case 4: return run_take<uint32_t>(dev, src, src_len, idx, out, m, vsrc, vout);
+    case 2: return run_take<uint16_t>(dev, src, src_len, idx, out, m, vsrc, vout);
+    case 1: return run_take<uint8_t>(dev, src, src_len, idx, out, m, vsrc, vout);
+    default: return AGPU_EUNSUPPORTED;
+  }
+}
+
+extern "C" int agpu_put(agpu_device* dev, int dtype, const void* src, const uint32_t* src_idx, void* dst,
+                        const uint32_t* dst_idx, size_t m) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (m && (!src || !src_idx || !dst || !dst_idx)) return AGPU_EINVAL;
+  if (m == 0) return 0;
+  const unsigned grid = (unsigned)ceil_div(m, (size_t)kBlock);
+  if (dtype == AGPU_BOOL) {
+    AGPU_LAUNCH(dev, put_bits_kernel, grid, kBlock, 0, (const uint32_t*)src, src_idx, (uint32_t*)dst, dst_idx, m);
+    return agpu_finish_launch();
+  }
+  switch (agpu_dtype_size(dtype)) {
+    case 4: AGPU_LAUNCH(dev, put_kernel<uint32_t>, grid, kBlock, 0, (const uint32_t*)src, src_idx, (uint32_t*)dst, dst_idx, m); break;
+    case 2: AGPU_LAUNCH(dev, put_kernel<uint16_t>, grid, kBlock, 0, (const uint16_t*)src, src_idx, (uint16_t*)dst, dst_idx, m); break;
+    case 1: AGPU_LAUNCH(dev, put_kernel<uint8_t>, grid, kBlock, 0, (const uint8_t*)src, src_idx, (uint8_t*)dst, dst_idx, m); break;
+    default: return AGPU_EUNSUPPORTED;
+  }
+  return agpu_finish_launch();
+}
+
+extern "C" size_t agpu_filter_scratch_bytes(size_t n) {
+  const size_t tiles = filter_tiles(n);
+  return ((tiles * 8 + 15) / 16) * 16 + ((tiles * 4 + 15) / 16) * 16 + 16;
+}
+
+extern "C" int agpu_filter_count(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n,
+                                 void* scratch, uint64_t* total_dev) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!scratch || !total_dev || (n && !mask)) return AGPU_EINVAL;
+  AGPU_CUDA(cudaMemsetAsync(total_dev, 0, 8, dev->stream));
+  if (n == 0) return 0;
+  const FilterScratch sc = filter_scratch(scratch, n);
+  const size_t tiles = filter_tiles(n);
+  const size_t grid = ceil_div(tiles, (size_t)(kBlock / 32));
+  if (grid > 0x7FFFFFFFull) return AGPU_EINVAL;
+  AGPU_LAUNCH(dev, filter_count_kernel, (unsigned)grid, kBlock, 0, mask, vmask, n, sc.counts,
+              (unsigned long long*)total_dev);
+  return agpu_finish_launch();
+}
+
+extern "C" int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src, const uint32_t* vsrc,
+                                   const uint32_t* mask, const uint32_t* vmask, size_t n, void* scratch,
+                                   void* out, uint32_t* vout) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (n && (!src || !mask || !scratch || !out)) return AGPU_EINVAL;
+  if (n == 0) return 0;
+  const FilterScratch sc = filter_scratch(scratch, n);
+  AGPU_LAUNCH(dev, filter_scan_kernel, 1, 1024, 0, sc.counts, sc.offsets, filter_tiles(n));
+  int rc = agpu_finish_launch();
+  if (rc) return rc;
+  switch (agpu_dtype_size(dtype)) {
+    case 4: return run_filter<uint32_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
+    case 2: return run_filter<uint16_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
+    case 1: return run_filter<uint8_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
+    default: return AGPU_EUNSUPPORTED;
+  }
+}

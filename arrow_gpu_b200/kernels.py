@@ -1,0 +1,659 @@
+"""Operator layer: the host-side mirror of the reference's operator crates
+(`arithmetic`, `compare`, `logical`, `cast`, `math`, `trigonometry`, `routines`).
+
+Every trait method of the reference exists here under the same name in two forms, like the
+reference: the eager form (`a.add(b)`) and the recording form (`a.add_op(b, pipeline)`), plus the
+`*_dyn` / `*_op_dyn` free functions that dispatch on the runtime array type and raise `Panic`
+for unsupported pairs (the reference `panic!`s).  Each call is ONE kernel launch through the
+C ABI (include/agpu.h): value kernel and validity-bitmap kernel of the reference are fused.
+
+Nothing here computes on the host; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check, lib
+from .array import (ARRAY_TYPES, ArrowComputePipeline, ArrowType, BooleanArrayGPU, Date32ArrayGPU,
+                    Float32ArrayGPU, Int8ArrayGPU, Int16ArrayGPU, Int32ArrayGPU, NullBitBufferGpu, Panic,
+                    PrimitiveArrayGpu, UInt8ArrayGPU, UInt16ArrayGPU, UInt32ArrayGPU, _new_validity, _vptr,
+                    bitmap_words)
+
+_INT_TYPES = (Int32ArrayGPU, UInt32ArrayGPU, Int16ArrayGPU, UInt16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU)
+_I32_BACKED = (Int32ArrayGPU, Date32ArrayGPU)
+
+
+def _pipeline_for(arr) -> ArrowComputePipeline:
+    return ArrowComputePipeline(arr.get_gpu_device(), None)
+
+
+def _eager(op_fn):
+    """default_impl! of the reference: new pipeline -> *_op -> finish"""
+    def run(self, *args):
+        pipeline = _pipeline_for(self)
+        out = op_fn(self, *args, pipeline)
+        pipeline.finish()
+        return out
+    return run
+
+
+def _check_same_len(a, b, what):
+    if a.len != b.len:
+        raise Panic(f"{what}: length mismatch {a.len} vs {b.len}")
+
+
+# ==========================================================================================
+# low-level launchers (one C-ABI call each)
+# ==========================================================================================
+def _binary(op: int, a: PrimitiveArrayGpu, b: PrimitiveArrayGpu, out_cls=None, what="binary"):
+    _check_same_len(a, b, what)
+    dev = a.gpu_device
+    out_cls = out_cls or type(a)
+    nb = _new_validity(dev, a.len, a.null_buffer, b.null_buffer)
+    out = out_cls.empty(a.len, dev, nb)
+    check(lib().agpu_binary(dev.handle, op, a.DTYPE, a.data.ptr, b.data.ptr, out.data.ptr, a.len,
+                            _vptr(a.null_buffer), _vptr(b.null_buffer), _vptr(nb)), what)
+    return out
+
+
+def _scalar(op: int, a: PrimitiveArrayGpu, s: PrimitiveArrayGpu, what="scalar"):
+    """rhs is a 1-element array; validity of `a` is copied (arithmetic/src/lib.rs:35-38)"""
+    if s.len != 1:
+        raise Panic(f"{what}: scalar operand must have exactly one element")
+    dev = a.gpu_device
+    nb = _new_validity(dev, a.len, a.null_buffer)
+    out = type(a).empty(a.len, dev, nb)
+    check(lib().agpu_scalar(dev.handle, op, a.DTYPE, a.data.ptr, s.data.ptr, out.data.ptr, a.len,
+                            _vptr(a.null_buffer), _vptr(nb)), what)
+    return out
+
+
+def _unary(op: int, a: PrimitiveArrayGpu, out_cls=None, what="unary"):
+    dev = a.gpu_device
+    out_cls = out_cls or type(a)
+    nb = _new_validity(dev, a.len, a.null_buffer)
+    out = out_cls.empty(a.len, dev, nb)
+    check(lib().agpu_unary(dev.handle, op, a.DTYPE, a.data.ptr, out.data.ptr, a.len,
+                           _vptr(a.null_buffer), _vptr(nb)), what)
+    return out
+
+
+def _compare(op: int, a: PrimitiveArrayGpu, b: PrimitiveArrayGpu, what="compare") -> BooleanArrayGPU:
+    _check_same_len(a, b, what)
+    dev = a.gpu_device
+    nb = _new_validity(dev, a.len, a.null_buffer, b.null_buffer)
+    out = BooleanArrayGPU.empty(a.len, dev, nb)
+    check(lib().agpu_compare(dev.handle, op, a.DTYPE, a.data.ptr, b.data.ptr, out.data.ptr, a.len,
+                             _vptr(a.null_buffer), _vptr(b.null_buffer), _vptr(nb)), what)
+    return out
+
+
+def _shift(op: int, a: PrimitiveArrayGpu, counts: UInt32ArrayGPU, what="shift"):
+    _check_same_len(a, counts, what)
+    dev = a.gpu_device
+    nb = _new_validity(dev, a.len, a.null_buffer, counts.null_buffer)
+    out = type(a).empty(a.len, dev, nb)
+    check(lib().agpu_shift(dev.handle, op, a.DTYPE, a.data.ptr, counts.data.ptr, out.data.ptr, a.len,
+                           _vptr(a.null_buffer), _vptr(counts.null_buffer), _vptr(nb)), what)
+    return out
+
+
+# ==========================================================================================
+# arithmetic  (crates/arithmetic/src/arithmetic_kernels.rs, lib.rs, aggregate_kernels.rs)
+# ==========================================================================================
+_SCALAR_OPS = {"add": _ffi.ADD, "sub": _ffi.SUB, "mul": _ffi.MUL, "div": _ffi.DIV, "rem": _ffi.REM}
+
+# scalar + : f32, i32, u32, Date32, u16 ; - * / % : f32, i32, u32, Date32  (SURVEY.md §2.2).
+# i8/u8/i16 (+ u16 - * / %) are new surface required by BASELINE.json config 2.
+_SCALAR_TYPES = (Float32ArrayGPU, Int32ArrayGPU, UInt32ArrayGPU, Date32ArrayGPU, UInt16ArrayGPU,
+                 Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU)
+
+
+def _scalar_compatible(a, s) -> bool:
+    if type(a) is type(s):
+        return True
+    return isinstance(a, _I32_BACKED) and isinstance(s, _I32_BACKED)  # T: Int32Type (types.rs)
+
+
+def _make_scalar(name, op):
+    def scalar_op(self, value, pipeline):
+        if not isinstance(self, _SCALAR_TYPES) or not _scalar_compatible(self, value):
+            raise Panic(f"Operation {name}_scalar not supported for type {self.get_dtype()} {value.get_dtype()}")
+        return _scalar(op, self, value, f"{name}_scalar")
+    return scalar_op
+
+
+for _n, _o in _SCALAR_OPS.items():
+    _fn = _make_scalar(_n, _o)
+    setattr(PrimitiveArrayGpu, f"{_n}_scalar_op", _fn)        # ArrowScalarAdd::add_scalar_op ...
+    setattr(PrimitiveArrayGpu, f"{_n}_scalar", _eager(_fn))    # ArrowScalarAdd::add_scalar ...
+
+_ARRAY_OPS = {"add": _ffi.ADD, "sub": _ffi.SUB, "mul": _ffi.MUL, "div": _ffi.DIV}
+
+
+def _array_result_cls(a, b):
+    """i32 + Date32 pairs give the type of `self` (impl for T: Int32Type, arithmetic/src/i32.rs:103-119);
+    add_array_dyn maps (Int32, Date32) to self.add_op, so the result is typed like the lhs."""
+    return type(a)
+
+
+def _make_array(name, op):
+    def array_op(self, value, pipeline):
+        same = type(self) is type(value) or (isinstance(self, _I32_BACKED) and isinstance(value, _I32_BACKED))
+        if not same or isinstance(self, BooleanArrayGPU):
+            raise Panic(f"Operation {name} not supported for type {self.get_dtype()} {value.get_dtype()}")
+        return _binary(op, self, value, _array_result_cls(self, value), name)
+    return array_op
+
+
+for _n, _o in _ARRAY_OPS.items():
+    _fn = _make_array(_n, _o)
+    setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)       # ArrowAdd::add_op ...
+    setattr(PrimitiveArrayGpu, _n, _eager(_fn))        # ArrowAdd::add ...
+
+
+def _neg_op(self, pipeline):
+    if not isinstance(self, Float32ArrayGPU):
+        raise Panic(f"Operation neg_dyn not supported for type {self.get_dtype()}")
+    return _unary(_ffi.NEG, self, what="neg")
+
+
+PrimitiveArrayGpu.neg_op = _neg_op
+PrimitiveArrayGpu.neg = _eager(_neg_op)
+
+
+def _sum_op(self, pipeline):
+    """Sum::sum_op (aggregate_kernels.rs:24-52): one-element array, validity ignored"""
+    if not isinstance(self, (Float32ArrayGPU, Int32ArrayGPU, UInt32ArrayGPU)):
+        raise Panic(f"Operation sum not supported for type {self.get_dtype()}")
+    dev = self.gpu_device
+    out = type(self).empty(1, dev)
+    check(lib().agpu_sum(dev.handle, self.DTYPE, self.data.ptr, self.len, out.data.ptr), "sum")
+    return out
+
+
+PrimitiveArrayGpu.sum_op = _sum_op
+PrimitiveArrayGpu.sum = _eager(_sum_op)
+
+
+def _dyn2(method_name, doc=""):
+    """(fn_dyn, fn_op_dyn) pair dispatching to a two-operand method"""
+    def op_dyn(data_1, data_2, pipeline):
+        return getattr(data_1, method_name)(data_2, pipeline)
+
+    def dyn(data_1, data_2):
+        pipeline = _pipeline_for(data_1)
+        out = op_dyn(data_1, data_2, pipeline)
+        pipeline.finish()
+        return out
+    dyn.__doc__ = op_dyn.__doc__ = doc
+    return dyn, op_dyn
+
+
+def _dyn1(method_name, doc=""):
+    def op_dyn(data, pipeline):
+        return getattr(data, method_name)(pipeline)
+
+    def dyn(data):
+        pipeline = _pipeline_for(data)
+        out = op_dyn(data, pipeline)
+        pipeline.finish()
+        return out
+    dyn.__doc__ = op_dyn.__doc__ = doc
+    return dyn, op_dyn
+
+
+add_scalar_dyn, add_scalar_op_dyn = _dyn2("add_scalar_op", "Add a scalar to each element in the array")
+sub_scalar_dyn, sub_scalar_op_dyn = _dyn2("sub_scalar_op", "Subtract a scalar from each element in the array")
+mul_scalar_dyn, mul_scalar_op_dyn = _dyn2("mul_scalar_op", "Multiply a scalar to each element in the array")
+div_scalar_dyn, div_scalar_op_dyn = _dyn2("div_scalar_op", "Divide each element in the array by scalar")
+rem_scalar_dyn, rem_scalar_op_dyn = _dyn2("rem_scalar_op", "Find remainder of each element in the array by scalar")
+add_array_dyn, add_array_op_dyn = _dyn2("add_op", "Compute x + y for each pair (x, y) in zip(lhs, rhs)")
+sub_array_dyn, sub_array_op_dyn = _dyn2("sub_op", "Compute x - y for each pair (x, y) in zip(lhs, rhs)")
+mul_array_dyn, mul_array_op_dyn = _dyn2("mul_op", "Compute x * y for each pair (x, y) in zip(lhs, rhs)")
+div_array_dyn, div_array_op_dyn = _dyn2("div_op", "Compute x / y for each pair (x, y) in zip(lhs, rhs)")
+neg_dyn, neg_op_dyn = _dyn1("neg_op")
+
+
+def _len_routed(array_op_dyn, scalar_op_dyn):
+    """add_dyn & co route by operand length (arithmetic_kernels.rs:101-119): both len 1 or both
+    != 1 -> array op; exactly one of length 1 -> scalar op with that operand as the scalar."""
+    def op_dyn(input1, input2, pipeline):
+        x, y = input1.len, input2.len
+        if (x == 1 and y == 1) or (x != 1 and y != 1):
+            return array_op_dyn(input1, input2, pipeline)
+        if y == 1:
+            return scalar_op_dyn(input1, input2, pipeline)
+        return scalar_op_dyn(input2, input1, pipeline)
+
+    def dyn(input1, input2):
+        pipeline = _pipeline_for(input1)
+        out = op_dyn(input1, input2, pipeline)
+        pipeline.finish()
+        return out
+    return dyn, op_dyn
+
+
+add_dyn, add_op_dyn = _len_routed(add_array_op_dyn, add_scalar_op_dyn)
+sub_dyn, sub_op_dyn = _len_routed(sub_array_op_dyn, sub_scalar_op_dyn)
+mul_dyn, mul_op_dyn = _len_routed(mul_array_op_dyn, mul_scalar_op_dyn)
+div_dyn, div_op_dyn = _len_routed(div_array_op_dyn, div_scalar_op_dyn)
+
+# ==========================================================================================
+# compare  (crates/compare/src/lib.rs)
+# ==========================================================================================
+_CMP = {"gt": _ffi.GT, "gteq": _ffi.GTEQ, "lt": _ffi.LT, "lteq": _ffi.LTEQ, "eq": _ffi.EQ}
+
+
+def _make_cmp(name, op):
+    def cmp_op(self, operand, pipeline):
+        if type(self) is not type(operand) or isinstance(self, BooleanArrayGPU):
+            raise Panic(f"Operation {name}_dyn not supported for type {self.get_dtype()} {operand.get_dtype()}")
+        return _compare(op, self, operand, name)
+    return cmp_op
+
+
+for _n, _o in _CMP.items():
+    _fn = _make_cmp(_n, _o)
+    setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)     # Compare::gt_op ...
+    setattr(PrimitiveArrayGpu, _n, _eager(_fn))      # Compare::gt ...
+
+gt_dyn, gt_op_dyn = _dyn2("gt_op", "Construct bool array from computing x > y for each pair (x, y)")
+gteq_dyn, gteq_op_dyn = _dyn2("gteq_op", "Construct bool array from computing x >= y for each pair (x, y)")
+lt_dyn, lt_op_dyn = _dyn2("lt_op", "Construct bool array from computing x < y for each pair (x, y)")
+lteq_dyn, lteq_op_dyn = _dyn2("lteq_op", "Construct bool array from computing x <= y for each pair (x, y)")
+eq_dyn, eq_op_dyn = _dyn2("eq_op", "Construct bool array from computing x == y for each pair (x, y)")
+
+
+def _make_minmax(name, op):
+    def mm_op(self, operand, pipeline):
+        if type(self) is not type(operand) or isinstance(self, BooleanArrayGPU):
+            raise Panic(f"Operation {name}_dyn not supported for type {self.get_dtype()} {operand.get_dtype()}")
+        return _binary(op, self, operand, what=name)
+    return mm_op
+
+
+for _n, _o in {"min": _ffi.MIN, "max": _ffi.MAX}.items():
+    _fn = _make_minmax(_n, _o)
+    setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)     # MinMax::min_op / max_op
+    setattr(PrimitiveArrayGpu, _n, _eager(_fn))
+
+min_dyn, min_op_dyn = _dyn2("min_op", "Compute min(x, y) for each pair (x, y) in zip(lhs, rhs)")
+max_dyn, max_op_dyn = _dyn2("max_op", "Compute max(x, y) for each pair (x, y) in zip(lhs, rhs)")
+
+# ==========================================================================================
+# logical  (crates/logical/src/lib.rs, boolean.rs)
+# ==========================================================================================
+_LOGICAL = {"bitwise_and": _ffi.AND, "bitwise_or": _ffi.OR, "bitwise_xor": _ffi.XOR}
+
+
+def _make_logical(name, op):
+    def logical_op(self, operand, pipeline):
+        if type(self) is not type(operand) or not isinstance(self, _INT_TYPES):
+            raise Panic(f"Operation {name}_dyn not supported for type {self.get_dtype()} {operand.get_dtype()}")
+        return _binary(op, self, operand, what=name)
+    return logical_op
+
+
+for _n, _o in _LOGICAL.items():
+    _fn = _make_logical(_n, _o)
+    setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)
+    setattr(PrimitiveArrayGpu, _n, _eager(_fn))
+
+
+def _not_op(self, pipeline):
+    if not isinstance(self, _INT_TYPES):
+        raise Panic(f"Operation bitwise_not_dyn not supported for type {self.get_dtype()}")
+    return _unary(_ffi.NOT, self, what="bitwise_not")
+
+
+PrimitiveArrayGpu.bitwise_not_op = _not_op
+PrimitiveArrayGpu.bitwise_not = _eager(_not_op)
+
+
+def _make_shift(name, op):
+    def shift_op(self, operand, pipeline):
+        if not isinstance(self, _INT_TYPES) or not isinstance(operand, UInt32ArrayGPU):
+            raise Panic(f"Operation {name}_dyn not supported for type {self.get_dtype()} {operand.get_dtype()}")
+        return _shift(op, self, operand, name)
+    return shift_op
+
+
+for _n, _o in {"bitwise_shl": _ffi.SHL, "bitwise_shr": _ffi.SHR}.items():
+    _fn = _make_shift(_n, _o)
+    setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)
+    setattr(PrimitiveArrayGpu, _n, _eager(_fn))
+
+
+def _make_bool_logical(name, op):
+    def bool_op(self, operand, pipeline):
+        if not isinstance(operand, BooleanArrayGPU):
+            raise Panic(f"Operation {name}_dyn not supported for type {self.get_dtype()} {operand.get_dtype()}")
+        _check_same_len(self, operand, name)
+        dev = self.gpu_device
+        nb = _new_validity(dev, self.len, self.null_buffer, operand.null_buffer)
+        out = BooleanArrayGPU.empty(self.len, dev, nb)
+        check(lib().agpu_bitmap_binary(dev.handle, op, self.data.ptr, operand.data.ptr, out.data.ptr, self.len,
+                                       _vptr(self.null_buffer), _vptr(operand.null_buffer), _vptr(nb)), name)
+        return out
+    return bool_op
+
+
+for _n, _o in _LOGICAL.items():
+    _fn = _make_bool_logical(_n, _o)
+    setattr(BooleanArrayGPU, f"{_n}_op", _fn)
+    setattr(BooleanArrayGPU, _n, _eager(_fn))
+
+
+def _bool_not_op(self, pipeline):
+    dev = self.gpu_device
+    nb = _new_validity(dev, self.len, self.null_buffer)
+    out = BooleanArrayGPU.empty(self.len, dev, nb)
+    check(lib().agpu_bitmap_not(dev.handle, self.data.ptr, out.data.ptr, self.len, _vptr(self.null_buffer),
+                                _vptr(nb)), "bitwise_not")
+    return out
+
+
+BooleanArrayGPU.bitwise_not_op = _bool_not_op
+BooleanArrayGPU.bitwise_not = _eager(_bool_not_op)
+
+
+def _bool_shift_unsupported(self, operand, pipeline=None):
+    raise Panic("shift is not defined for BooleanArrayGPU (empty shader, logical/src/boolean.rs:14)")
+
+
+BooleanArrayGPU.bitwise_shl_op = BooleanArrayGPU.bitwise_shr_op = _bool_shift_unsupported
+BooleanArrayGPU.bitwise_shl = BooleanArrayGPU.bitwise_shr = _bool_shift_unsupported
+
+
+def _bool_reduce(fn_name):
+    def run(self) -> bool:
+        """LogicalContains (logical/src/boolean.rs:106-147); validity is ignored like the reference"""
+        dev = self.gpu_device
+        flag = dev.create_empty_buffer(4)
+        check(getattr(lib(), fn_name)(dev.handle, self.data.ptr, self.len, flag.ptr), fn_name)
+        return bool(dev.retrive_data(flag, 4).view(np.uint32)[0])
+    return run
+
+
+BooleanArrayGPU.any = _bool_reduce("agpu_any")
+BooleanArrayGPU.all = _bool_reduce("agpu_all")
+
+bitwise_and_dyn, bitwise_and_op_dyn = _dyn2("bitwise_and_op", "Compute x & y for each pair (x, y)")
+bitwise_or_dyn, bitwise_or_op_dyn = _dyn2("bitwise_or_op", "Compute x | y for each pair (x, y)")
+bitwise_xor_dyn, bitwise_xor_op_dyn = _dyn2("bitwise_xor_op", "Compute x ^ y for each pair (x, y)")
+bitwise_shl_dyn, bitwise_shl_op_dyn = _dyn2("bitwise_shl_op", "Compute x << y for each pair (x, y)")
+bitwise_shr_dyn, bitwise_shr_op_dyn = _dyn2("bitwise_shr_op", "Compute x >> y for each pair (x, y)")
+bitwise_not_dyn, bitwise_not_op_dyn = _dyn1("bitwise_not_op", "Compute !x for each x in array")
+
+# ==========================================================================================
+# cast  (crates/cast/src/lib.rs)
+# ==========================================================================================
+# the matrix of cast_dyn (cast/src/lib.rs:135-161)
+_CAST_MATRIX = {
+    Int8ArrayGPU: (UInt8ArrayGPU, UInt16ArrayGPU, UInt32ArrayGPU, Int16ArrayGPU, Int32ArrayGPU, Float32ArrayGPU),
+    Int16ArrayGPU: (Int32ArrayGPU, UInt16ArrayGPU, UInt32ArrayGPU, Float32ArrayGPU),
+    UInt8ArrayGPU: (UInt16ArrayGPU, UInt32ArrayGPU, Int8ArrayGPU, Int16ArrayGPU, Int32ArrayGPU, Float32ArrayGPU),
+    UInt16ArrayGPU: (UInt32ArrayGPU, Int16ArrayGPU, Int32ArrayGPU, Float32ArrayGPU),
+    Float32ArrayGPU: (UInt8ArrayGPU,),
+    BooleanArrayGPU: (Float32ArrayGPU,),
+}
+
+
+def _cast_to(self, into_cls, pipeline, matrix=_CAST_MATRIX, what="cast"):
+    if into_cls not in matrix.get(type(self), ()):
+        raise Panic(f"Casting not supported for type {self.get_dtype()} {into_cls.ARROW_TYPE}")
+    dev = self.gpu_device
+    nb = _new_validity(dev, self.len, self.null_buffer)
+    out = into_cls.empty(self.len, dev, nb)
+    check(lib().agpu_cast(dev.handle, self.DTYPE, into_cls.DTYPE, self.data.ptr, out.data.ptr, self.len,
+                          _vptr(self.null_buffer), _vptr(nb)), what)
+    return out
+
+
+def _cast_op(self, into, pipeline):
+    """Cast<T>::cast_op; `into` is the target array class or its ArrowType"""
+    return _cast_to(self, ARRAY_TYPES[into] if isinstance(into, ArrowType) else into, pipeline)
+
+
+def _bitcast_op(self, into, pipeline):
+    """BitCast<T>::bitcast_op — only u32 -> f32 exists (cast/src/lib.rs:187-192)"""
+    cls = ARRAY_TYPES[into] if isinstance(into, ArrowType) else into
+    return _cast_to(self, cls, pipeline, {UInt32ArrayGPU: (Float32ArrayGPU,)}, "bitcast")
+
+
+for _cls in (PrimitiveArrayGpu, BooleanArrayGPU):
+    _cls.cast_op = _cast_op
+    _cls.cast = _eager(_cast_op)
+PrimitiveArrayGpu.bitcast_op = _bitcast_op
+PrimitiveArrayGpu.bitcast = _eager(_bitcast_op)
+
+cast_dyn, cast_op_dyn = _dyn2("cast_op", "Cast x as `T` for each x in array")
+bitcast_dyn, bitcast_op_dyn = _dyn2("bitcast_op", "Reinterpret x as `T` for each x in array")
+
+# ==========================================================================================
+# math  (crates/math/src/lib.rs)   trigonometry  (crates/trigonometry/src/lib.rs)
+# ==========================================================================================
+_FLOAT_UNARY = {"sqrt": _ffi.SQRT, "cbrt": _ffi.CBRT, "exp": _ffi.EXP, "exp2": _ffi.EXP2, "log": _ffi.LOG,
+                "log2": _ffi.LOG2}
+
+
+def _make_float_unary(name, op):
+    def fn(self, pipeline):
+        if not isinstance(self, Float32ArrayGPU):
+            raise Panic(f"Operation {name}_dyn not supported for type {self.get_dtype()}")
+        return _unary(op, self, what=name)
+    return fn
+
+
+for _n, _o in _FLOAT_UNARY.items():
+    _fn = _make_float_unary(_n, _o)
+    setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)    # FloatMathUnary::sqrt_op ...
+    setattr(PrimitiveArrayGpu, _n, _eager(_fn))
+
+
+def _abs_op(self, pipeline):
+    if not isinstance(self, (Float32ArrayGPU, Int32ArrayGPU)):
+        raise Panic(f"Operation abs_dyn not supported for type {self.get_dtype()}")
+    return _unary(_ffi.ABS, self, what="abs")
+
+
+def _power_op(self, other, pipeline):
+    if type(self) is not type(other) or not isinstance(self, (Float32ArrayGPU, Int32ArrayGPU)):
+        raise Panic(f"Operation power_dyn not supported for type {self.get_dtype()} {other.get_dtype()}")
+    return _binary(_ffi.POW, self, other, what="power")
+
+
+PrimitiveArrayGpu.abs_op = _abs_op
+PrimitiveArrayGpu.abs = _eager(_abs_op)
+PrimitiveArrayGpu.power_op = _power_op
+PrimitiveArrayGpu.power = _eager(_power_op)
+
+abs_dyn, abs_op_dyn = _dyn1("abs_op", "Compute abs(x) for each x in array")
+sqrt_dyn, sqrt_op_dyn = _dyn1("sqrt_op", "Compute square_root(x) for each x in array")
+cbrt_dyn, cbrt_op_dyn = _dyn1("cbrt_op", "Compute cube_root(x) for each x in array")
+exp_dyn, exp_op_dyn = _dyn1("exp_op", "Compute e^x for each x in array")
+exp2_dyn, exp2_op_dyn = _dyn1("exp2_op", "Compute 2^x for each x in array")
+log_dyn, log_op_dyn = _dyn1("log_op", "Compute log(x) for each x in array")
+log2_dyn, log2_op_dyn = _dyn1("log2_op", "Compute log_to_base_2(x) for each x in array")
+power_dyn, power_op_dyn = _dyn2("power_op", "Compute x ^ y for each pair (x, y) in zip(self, other)")
+
+_TRIG_INT = (Int8ArrayGPU, UInt8ArrayGPU, Int16ArrayGPU, UInt16ArrayGPU)
+
+
+def _make_trig(name, op, allow_int):
+    def fn(self, pipeline):
+        ok = isinstance(self, Float32ArrayGPU) or (allow_int and isinstance(self, _TRIG_INT))
+        if not ok:
+            raise Panic(f"Operation {name}_op_dyn not supported for type {self.get_dtype()}")
+        return _unary(op, self, Float32ArrayGPU, name)   # int columns: cast fused into the kernel
+    return fn
+
+
+for _n, _o, _ai in (("sin", _ffi.SIN, True), ("cos", _ffi.COS, True), ("acos", _ffi.ACOS, False),
+                    ("sinh", _ffi.SINH, True)):
+    _fn = _make_trig(_n, _o, _ai)
+    setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)    # Trigonometric::sin_op ..., Hyperbolic::sinh_op
+    setattr(PrimitiveArrayGpu, _n, _eager(_fn))
+
+sin_dyn, sin_op_dyn = _dyn1("sin_op", "Compute sin(x) for each x in array")
+cos_dyn, cos_op_dyn = _dyn1("cos_op", "Compute cos(x) for each x in array")
+acos_dyn, acos_op_dyn = _dyn1("acos_op", "Compute acos(x) for each x in array")
+sinh_dyn, sinh_op_dyn = _dyn1("sinh_op", "Compute sinh(x) for each x in array")
+
+# ==========================================================================================
+# routines  (crates/routines/src/lib.rs, merge.rs, take.rs, put.rs, bool.rs)
+# ==========================================================================================
+_TAKE_PUT_TYPES = (Date32ArrayGPU, UInt32ArrayGPU, Int32ArrayGPU, Float32ArrayGPU, BooleanArrayGPU,
+                   # 8/16-bit take/put are `todo!()` in the reference (routines/src/i16.rs:5-6): new surface
+                   Int16ArrayGPU, UInt16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU)
+
+
+def _merge_op(self, other, mask, pipeline):
+    """Swizzle::merge_op (routines/src/lib.rs:82-120, bool.rs:49-87) + merge_null_buffers_op"""
+    if type(self) is not type(other) or not isinstance(mask, BooleanArrayGPU):
+        raise Panic(f"Merge Operation not supported between {self.get_dtype()} and {other.get_dtype()}")
+    _check_same_len(self, other, "merge")
+    _check_same_len(self, mask, "merge")
+    dev = self.gpu_device
+    nb = _new_validity(dev, self.len, self.null_buffer, other.null_buffer, mask.null_buffer)
+    out = type(self).empty(self.len, dev, nb)
+    check(lib().agpu_merge(dev.handle, self.DTYPE, self.data.ptr, other.data.ptr, mask.data.ptr, out.data.ptr,
+                           self.len, _vptr(self.null_buffer), _vptr(other.null_buffer),
+                           _vptr(mask.null_buffer), _vptr(nb)), "merge")
+    return out
+
+
+def _take_op(self, indexes, pipeline):
+    """Swizzle::take_op (lib.rs:122-143, bool.rs:89-100); result length = indexes.len (Q8)"""
+    if not isinstance(self, _TAKE_PUT_TYPES) or not isinstance(indexes, UInt32ArrayGPU):
+        raise Panic(f"Take Operation not supported for {self.get_dtype()}")
+    dev = self.gpu_device
+    nb = _new_validity(dev, indexes.len, self.null_buffer)
+    out = type(self).empty(indexes.len, dev, nb)
+    check(lib().agpu_take(dev.handle, self.DTYPE, self.data.ptr, self.len, indexes.data.ptr, out.data.ptr,
+                          indexes.len, _vptr(self.null_buffer), _vptr(nb)), "take")
+    return out
+
+
+def _put_op(self, src_indexes, dst, dst_indexes, pipeline):
+    """Swizzle::put_op (lib.rs:145-170): scatter into `dst` in place; arrays with validity are
+    `todo!()` in the reference and rejected here"""
+    if type(self) is not type(dst) or not isinstance(self, _TAKE_PUT_TYPES):
+        raise Panic(f"Put Operation not supported for {self.get_dtype()} and {dst.get_dtype()}")
+    if self.null_buffer is not None or dst.null_buffer is not None:
+        raise NotImplementedError("put with validity bitmaps is todo!() in the reference (routines/src/lib.rs:164-169)")
+    _check_same_len(src_indexes, dst_indexes, "put")
+    dev = self.gpu_device
+    check(lib().agpu_put(dev.handle, self.DTYPE, self.data.ptr, src_indexes.data.ptr, dst.data.ptr,
+                         dst_indexes.data.ptr, src_indexes.len), "put")
+
+
+def _filter_op(self, mask, pipeline):
+    """New surface (BASELINE.json config 5; the reference has no filter): keep rows whose mask
+    bit is set and valid, order preserving.  Needs the selected count on the host to size the
+    output — the one extra synchronisation of this op."""
+    if not isinstance(mask, BooleanArrayGPU) or isinstance(self, BooleanArrayGPU):
+        raise Panic(f"Filter Operation not supported for {self.get_dtype()}")
+    _check_same_len(self, mask, "filter")
+    dev = self.gpu_device
+    l = lib()
+    scratch = dev.create_empty_buffer(l.agpu_filter_scratch_bytes(self.len))
+    total = dev.create_empty_buffer(8)
+    check(l.agpu_filter_count(dev.handle, mask.data.ptr, _vptr(mask.null_buffer), self.len, scratch.ptr, total.ptr),
+          "filter_count")
+    count = int(dev.retrive_data(total, 8).view(np.uint64)[0])
+    out = type(self).empty(count, dev)
+    vout = None
+    if self.null_buffer is not None:
+        vout = dev.create_empty_buffer(bitmap_words(self.len) * 4 + 4)
+        out.null_buffer = NullBitBufferGpu(vout, count, dev)
+    check(l.agpu_filter_scatter(dev.handle, self.DTYPE, self.data.ptr, _vptr(self.null_buffer), mask.data.ptr,
+                                _vptr(mask.null_buffer), self.len, scratch.ptr, out.data.ptr,
+                                vout.ptr if vout else None), "filter_scatter")
+    return out
+
+
+for _cls in (PrimitiveArrayGpu, BooleanArrayGPU):
+    _cls.merge_op = _merge_op
+    _cls.merge = _eager(_merge_op)
+    _cls.take_op = _take_op
+    _cls.take = _eager(_take_op)
+    _cls.put_op = _put_op
+    _cls.put = _eager(_put_op)
+PrimitiveArrayGpu.filter_op = _filter_op
+PrimitiveArrayGpu.filter = _eager(_filter_op)
+
+
+def merge_op_dyn(operand_1, operand_2, mask, pipeline):
+    return operand_1.merge_op(operand_2, mask, pipeline)
+
+
+def merge_dyn(operand_1, operand_2, mask):
+    pipeline = ArrowComputePipeline(operand_1.get_gpu_device(), "merge")
+    out = merge_op_dyn(operand_1, operand_2, mask, pipeline)
+    pipeline.finish()
+    return out
+
+
+def take_op_dyn(operand_1, indexes, pipeline):
+    return operand_1.take_op(indexes, pipeline)
+
+
+def take_dyn(operand_1, indexes):
+    pipeline = ArrowComputePipeline(operand_1.get_gpu_device(), "take")
+    out = take_op_dyn(operand_1, indexes, pipeline)
+    pipeline.finish()
+    return out
+
+
+def put_op_dyn(src, src_indexes, dst, dst_indexes, pipeline):
+    src.put_op(src_indexes, dst, dst_indexes, pipeline)
+
+
+def put_dyn(src, src_indexes, dst, dst_indexes):
+    pipeline = ArrowComputePipeline(src.get_gpu_device(), "put")
+    put_op_dyn(src, src_indexes, dst, dst_indexes, pipeline)
+    pipeline.finish()
+
+
+def filter_op_dyn(operand_1, mask, pipeline):
+    return operand_1.filter_op(mask, pipeline)
+
+
+def filter_dyn(operand_1, mask):
+    pipeline = ArrowComputePipeline(operand_1.get_gpu_device(), "filter")
+    out = filter_op_dyn(operand_1, mask, pipeline)
+    pipeline.finish()
+    return out
+
+
+# ==========================================================================================
+# fused expression (BASELINE.json config 3):  ((a * b) + c) > d  in one pass
+# ==========================================================================================
+def fused_mul_add_gt_op(a, b, c, d, pipeline) -> BooleanArrayGPU:
+    """Equivalent to gt_op_dyn(add_op_dyn(mul_op_dyn(a, b), c), d) on one pipeline
+    (the recorded-chain pattern of crates/arrow/examples/simple.rs:45-72), bit-identical to it,
+    in a single kernel: 16.75 B/row instead of 33.25 B/row."""
+    for x in (a, b, c, d):
+        if not isinstance(x, Float32ArrayGPU):
+            raise Panic(f"fused_mul_add_gt not supported for type {x.get_dtype()}")
+        _check_same_len(a, x, "fused_mul_add_gt")
+    dev = a.gpu_device
+    nb = _new_validity(dev, a.len, a.null_buffer, b.null_buffer, c.null_buffer, d.null_buffer)
+    out = BooleanArrayGPU.empty(a.len, dev, nb)
+    check(lib().agpu_fused_mul_add_gt(dev.handle, a.data.ptr, b.data.ptr, c.data.ptr, d.data.ptr, out.data.ptr,
+                                      a.len, _vptr(a.null_buffer), _vptr(b.null_buffer), _vptr(c.null_buffer),
+                                      _vptr(d.null_buffer), _vptr(nb)), "fused_mul_add_gt")
+    return out
+
+
+def fused_mul_add_gt(a, b, c, d) -> BooleanArrayGPU:
+    pipeline = _pipeline_for(a)
+    out = fused_mul_add_gt_op(a, b, c, d, pipeline)
+    pipeline.finish()
+    return out

@@ -1,0 +1,261 @@
+/*
+ * agpu.h — C ABI of the B200-native columnar compute path ("libagpu.so").
+ *
+ * This is the drop-in boundary for psvri/arrow-gpu's hot path.  Every entry point below
+ * replaces one seam of the reference's wgpu layer; the reference file:line it replaces is
+ * cited per function (paths relative to the reference root).  The reference's operator
+ * crates (arithmetic, compare, logical, cast, math, trigonometry, routines) call
+ *     ArrowComputePipeline::apply_{unary,binary,ternary,scalar,broadcast}_function
+ *         (crates/array/src/gpu_utils/compute_pipeline.rs:24-256)
+ * with a (WGSL source, entry point) pair; here the pair becomes an (op id, dtype id) pair
+ * and the wgpu::Buffer arguments become raw device pointers.  INTEGRATION.md shows the
+ * `extern "C"` block and `build.rs` the Rust crates would add.
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only, no C++/torch types; every function returns
+ *    0 on success, a positive cudaError_t, or a negative AGPU_E* code.  Nothing here
+ *    falls back to the CPU: without a CUDA device every compute call fails.
+ *  - value buffers hold `n` tightly packed little-endian elements of the dtype
+ *    (crates/array/src/array/primitive_array_gpu.rs:12-19).  Bitmaps (boolean data and
+ *    validity) are LSB-first bits packed in uint32 words, ceil(n/32) words long, bit i =
+ *    word i/32, mask 1<<(i%32) (== byte i/8, mask 1<<(i%8);
+ *    crates/array/src/array/null_bit_buffer.rs:47-49).  Validity 1 = valid.  A NULL
+ *    validity pointer means "no bitmap = all valid" (null_bit_buffer.rs:99-111).
+ *  - kernels read each input once and write each output once; bits >= n of every bitmap
+ *    word written are zero.
+ *  - all work is enqueued on the device handle's stream and returns without host
+ *    synchronisation (like ArrowComputePipeline::finish, compute_pipeline.rs:259-273);
+ *    only agpu_d2h / agpu_sync / agpu_event_elapsed_ms wait.
+ *  - fast paths need 16-byte aligned pointers (anything from agpu_alloc is 256-byte
+ *    aligned); other alignments take a slower element-wise kernel with identical results.
+ */
+#ifndef AGPU_H
+#define AGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGPU_ABI_VERSION 1
+
+/* dtype ids — crates/array/src/array/mod.rs:40-50 (enum ArrowType) */
+typedef enum {
+  AGPU_BOOL = 0,
+  AGPU_I8 = 1,
+  AGPU_I16 = 2,
+  AGPU_I32 = 3,
+  AGPU_U8 = 4,
+  AGPU_U16 = 5,
+  AGPU_U32 = 6,
+  AGPU_F32 = 7,
+  AGPU_DATE32 = 8 /* i32 storage, crates/array/src/array/date32_gpu.rs */
+} agpu_dtype;
+
+/* binary ops (array∘array and array∘scalar) */
+typedef enum {
+  AGPU_ADD = 0, /* arithmetic/compute_shaders/{f32,i32,u32}/array.wgsl, scalar.wgsl */
+  AGPU_SUB = 1,
+  AGPU_MUL = 2,
+  AGPU_DIV = 3,
+  AGPU_REM = 4,
+  AGPU_MIN = 5, /* compare/compute_shaders/ * /min_max.wgsl */
+  AGPU_MAX = 6,
+  AGPU_AND = 7, /* logical/compute_shaders/{i32,u32}/logical.wgsl */
+  AGPU_OR = 8,
+  AGPU_XOR = 9,
+  AGPU_POW = 10 /* math/compute_shaders/f32/floatbinary.wgsl, i32/binary.wgsl */
+} agpu_binop;
+
+/* unary ops */
+typedef enum {
+  AGPU_NEG = 0,   /* arithmetic/compute_shaders/f32/neg.wgsl */
+  AGPU_ABS = 1,   /* math f32/floatunary.wgsl:42, i32/unary.wgsl */
+  AGPU_NOT = 2,   /* logical {i32,u32}/not.wgsl */
+  AGPU_SQRT = 3,  /* math f32/floatunary.wgsl */
+  AGPU_CBRT = 4,
+  AGPU_EXP = 5,
+  AGPU_EXP2 = 6,
+  AGPU_LOG = 7,
+  AGPU_LOG2 = 8,
+  AGPU_SIN = 9,   /* trigonometry * /trigonometry.wgsl ; ints: fused cast->f32 */
+  AGPU_COS = 10,
+  AGPU_ACOS = 11,
+  AGPU_SINH = 12  /* trigonometry * /hyperbolic.wgsl */
+} agpu_unop;
+
+/* compare ops — compare/compute_shaders/ * /cmp.wgsl */
+typedef enum { AGPU_GT = 0, AGPU_GTEQ = 1, AGPU_LT = 2, AGPU_LTEQ = 3, AGPU_EQ = 4 } agpu_cmpop;
+
+/* shift ops — logical/compute_shaders/ * /shift.wgsl */
+typedef enum { AGPU_SHL = 0, AGPU_SHR = 1 } agpu_shiftop;
+
+/* error codes (negative; positive values are cudaError_t) */
+#define AGPU_OK 0
+#define AGPU_EUNSUPPORTED (-1) /* op/dtype pair the path does not define */
+#define AGPU_EINVAL (-2)       /* NULL where a pointer is required, bad size ... */
+#define AGPU_ENODEVICE (-3)    /* no CUDA device / device handle invalid */
+
+typedef struct agpu_device agpu_device; /* opaque: {ordinal, cudaStream_t, cudaMemPool_t} */
+typedef struct agpu_event agpu_event;   /* opaque cudaEvent_t wrapper */
+
+/* ---- device / buffer layer: replaces GpuDevice (crates/array/src/gpu_utils/gpu_device.rs) ---- */
+
+/* GpuDevice::new, gpu_device.rs:46-85 — opens CUDA device `ordinal`, creates one
+ * non-blocking stream and a stream-ordered memory pool that retains freed blocks. */
+int agpu_device_create(int ordinal, agpu_device** out);
+int agpu_device_destroy(agpu_device* dev);
+/* number of visible CUDA devices (0 when there is no driver/GPU) */
+int agpu_device_count(int* out);
+/* the cudaStream_t all work of this handle is ordered on (as void*) */
+void* agpu_device_stream(agpu_device* dev);
+int agpu_device_ordinal(agpu_device* dev);
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+uint64_t agpu_launch_count(agpu_device* dev);
+const char* agpu_error_string(int code);
+int agpu_abi_version(void);
+
+/* create_empty_buffer, gpu_device.rs:183-192 — stream-ordered, NOT zero-filled */
+int agpu_alloc(agpu_device* dev, size_t bytes, void** out);
+/* Drop of wgpu::Buffer — stream-ordered free, safe right after enqueueing work */
+int agpu_free(agpu_device* dev, void* ptr);
+/* create_gpu_buffer_with_data, gpu_device.rs:171-181 (host may be pageable or pinned) */
+int agpu_h2d(agpu_device* dev, void* dst_dev, const void* src_host, size_t bytes);
+/* retrive_data, gpu_device.rs:232-265 — copies and waits for the stream */
+int agpu_d2h(agpu_device* dev, void* dst_host, const void* src_dev, size_t bytes);
+/* clone_buffer / copy_buffer_to_buffer, gpu_device.rs:212-230, compute_pipeline.rs:275-300 */
+int agpu_d2d(agpu_device* dev, void* dst_dev, const void* src_dev, size_t bytes);
+int agpu_memset(agpu_device* dev, void* dst_dev, int byte_value, size_t bytes);
+/* device.poll(Wait) */
+int agpu_sync(agpu_device* dev);
+/* pinned host staging for from_slice / raw_values */
+int agpu_host_alloc(size_t bytes, void** out);
+int agpu_host_free(void* ptr);
+
+/* CmpQuery timestamp queries, crates/array/src/gpu_utils/compute_query.rs:3-90 */
+int agpu_event_create(agpu_event** out);
+int agpu_event_destroy(agpu_event* ev);
+int agpu_event_record(agpu_device* dev, agpu_event* ev);
+int agpu_event_elapsed_ms(agpu_event* start, agpu_event* stop, float* ms); /* waits for stop */
+
+/* ---- validity bitmaps: NullBitBufferGpu (crates/array/src/array/null_bit_buffer.rs) ---- */
+
+/* merge_null_bit_buffer[_op], null_bit_buffer.rs:168-243: vout = va & vb; a NULL side
+ * means all-valid (then vout = copy of the other side).  Both NULL -> AGPU_EINVAL
+ * (the reference returns None without touching the GPU). */
+int agpu_validity_and(agpu_device* dev, const uint32_t* va, const uint32_t* vb, uint32_t* vout,
+                      size_t n_bits);
+
+/* ---- arithmetic / min-max / logical / power, array ∘ array ----
+ * arithmetic/src/lib.rs:54-94 (impl_arithmetic_array_op), compare/src/lib.rs:113-140,164-172,
+ * logical/src/lib.rs:88-131, math/src/lib.rs:203-209.
+ * out[i] = a[i] op b[i]; if vout != NULL also vout = va & vb in the same pass. */
+int agpu_binary(agpu_device* dev, int op, int dtype, const void* a, const void* b, void* out,
+                size_t n, const uint32_t* va, const uint32_t* vb, uint32_t* vout);
+
+/* ---- array ∘ scalar: arithmetic/src/lib.rs:11-50 (impl_arithmetic_op) ----
+ * `scalar_dev` points at a 1-element device array, as in the reference where the rhs of
+ * *_scalar is a length-1 PrimitiveArrayGpu.  Validity is copied (lib.rs:35-38). */
+int agpu_scalar(agpu_device* dev, int op, int dtype, const void* a, const void* scalar_dev,
+                void* out, size_t n, const uint32_t* va, uint32_t* vout);
+
+/* ---- unary: neg / abs / not / f32 math / trig ----
+ * arithmetic_kernels.rs:296-319, math/src/lib.rs:195-237, logical/src/lib.rs:133-158,
+ * trigonometry/src/lib.rs:115-137.  For SIN/COS/SINH on i8/u8/i16/u16 the output is f32
+ * (cast fused, trigonometry/compute_shaders/{i8,u8,i16,u16}); otherwise out has `dtype`. */
+int agpu_unary(agpu_device* dev, int op, int dtype, const void* a, void* out, size_t n,
+               const uint32_t* va, uint32_t* vout);
+
+/* ---- compare -> packed bitmap: compare/src/lib.rs:85-111,142-162 ----
+ * bit i of out_bits = a[i] op b[i]; ceil(n/32) words written, padding bits zero. */
+int agpu_compare(agpu_device* dev, int op, int dtype, const void* a, const void* b,
+                 uint32_t* out_bits, size_t n, const uint32_t* va, const uint32_t* vb,
+                 uint32_t* vout);
+
+/* ---- shifts: logical/src/lib.rs:160-186; counts is a UInt32 column, one per row ---- */
+int agpu_shift(agpu_device* dev, int op, int dtype, const void* a, const uint32_t* counts,
+               void* out, size_t n, const uint32_t* va, const uint32_t* vcounts, uint32_t* vout);
+
+/* ---- bitmap (BooleanArrayGPU) logical: logical/src/boolean.rs:45-75 ----
+ * op in {AGPU_AND, AGPU_OR, AGPU_XOR}; padding bits of the last word are cleared. */
+int agpu_bitmap_binary(agpu_device* dev, int op, const uint32_t* a, const uint32_t* b,
+                       uint32_t* out, size_t n_bits, const uint32_t* va, const uint32_t* vb,
+                       uint32_t* vout);
+int agpu_bitmap_not(agpu_device* dev, const uint32_t* a, uint32_t* out, size_t n_bits,
+                    const uint32_t* va, uint32_t* vout);
+
+/* ---- casts: cast/src/lib.rs:40-87,135-161 (matrix), boolean_cast.rs, f32_cast.rs ----
+ * src/dst dtype pairs outside the reference matrix return AGPU_EUNSUPPORTED.
+ * For src == AGPU_BOOL `a` is a bitmap.  Same-width casts and bitcast are copies. */
+int agpu_cast(agpu_device* dev, int src_dtype, int dst_dtype, const void* a, void* out,
+              size_t n, const uint32_t* va, uint32_t* vout);
+
+/* ---- fused expression  ((a*b)+c) > d  on f32 columns (BASELINE.json config 3) ----
+ * One pass instead of mul_op_dyn -> add_op_dyn -> gt_op_dyn on a shared pipeline
+ * (crates/arrow/examples/simple.rs:45-72 pattern).  Bit-identical to the unfused chain:
+ * two roundings, no FMA contraction.  vout = va & vb & vc & vd (NULL = all valid). */
+int agpu_fused_mul_add_gt(agpu_device* dev, const float* a, const float* b, const float* c,
+                          const float* d, uint32_t* out_bits, size_t n, const uint32_t* va,
+                          const uint32_t* vb, const uint32_t* vc, const uint32_t* vd,
+                          uint32_t* vout);
+
+/* ---- routines: crates/routines ---- */
+
+/* Swizzle::merge_op, routines/src/lib.rs:82-120, bool.rs:49-87:
+ * out[i] = mask bit i ? a[i] : b[i]; dtype AGPU_BOOL merges bitmaps.
+ * validity (merge.rs:17-86): vout = ((va & m) | (vb & ~m)) & vmask with NULL = all ones
+ * (SURVEY.md Q7); vout may be NULL when va, vb and vmask are all NULL. */
+int agpu_merge(agpu_device* dev, int dtype, const void* a, const void* b, const uint32_t* mask,
+               void* out, size_t n, const uint32_t* va, const uint32_t* vb,
+               const uint32_t* vmask, uint32_t* vout);
+
+/* Swizzle::take_op, routines/src/lib.rs:122-143, take.rs:9-55, bool.rs:15-46:
+ * out[j] = src[idx[j]] for j < m; idx[j] >= src_len reads as zero (robust buffer access).
+ * dtype AGPU_BOOL gathers bits.  If vsrc != NULL, vout gets the gathered validity bits. */
+int agpu_take(agpu_device* dev, int dtype, const void* src, size_t src_len, const uint32_t* idx,
+              void* out, size_t m, const uint32_t* vsrc, uint32_t* vout);
+
+/* Swizzle::put_op, routines/src/lib.rs:145-170, put.rs:9-56, bool/put.wgsl:
+ * dst[dst_idx[i]] = src[src_idx[i]] in place, i < m (duplicate dst indices: any one wins). */
+int agpu_put(agpu_device* dev, int dtype, const void* src, const uint32_t* src_idx, void* dst,
+             const uint32_t* dst_idx, size_t m);
+
+/* filter / compaction (named by BASELINE.json config 5; not in the reference — SURVEY a18).
+ * Keeps rows whose mask bit is 1 and (if vmask) whose mask is valid, order preserving.
+ * Two calls so a sharded caller can learn the count (and exchange it between GPUs) before it
+ * allocates the output:
+ *   agpu_filter_count  : per-tile selected-row counts into `scratch`
+ *                        (agpu_filter_scratch_bytes(n) bytes, 16-byte aligned) and the total
+ *                        into *total_dev (a device uint64)
+ *   agpu_filter_scatter: scans the tile counts in `scratch`, then compacts the values into
+ *                        out[0 .. total) and, when vsrc and vout are given, the validity bits
+ *                        into vout (which must hold ceil(n/32) words; it is zeroed first). */
+size_t agpu_filter_scratch_bytes(size_t n);
+int agpu_filter_count(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n,
+                      void* scratch, uint64_t* total_dev);
+int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src, const uint32_t* vsrc,
+                        const uint32_t* mask, const uint32_t* vmask, size_t n, void* scratch,
+                        void* out, uint32_t* vout);
+
+/* ---- "next" rows ---- */
+
+/* Broadcast::broadcast_op, array/src/kernels/broadcast.rs:6-17, */
+/* array/compute_shaders/{f32,i32,u32}/broadcast.wgsl: out[i] = *scalar_host (by value bits) */
+int agpu_broadcast(agpu_device* dev, int dtype, const void* scalar_host, void* out, size_t n);
+
+/* Sum::sum_op, arithmetic/src/aggregate_kernels.rs:24-52 + */
+/* compute_shaders/{f32,i32,u32}/aggregate.wgsl: same 256-wide pairwise tree order, so the
+ * f32 result is bit-identical to the reference's.  out_dev: one element of dtype. */
+int agpu_sum(agpu_device* dev, int dtype, const void* a, size_t n, void* out_dev);
+
+/* LogicalContains::{any,all}, logical/src/boolean.rs:106-147: result_dev is a device
+ * uint32 (1/0).  `all` counts only the first n_bits. */
+int agpu_any(agpu_device* dev, const uint32_t* bits, size_t n_bits, uint32_t* result_dev);
+int agpu_all(agpu_device* dev, const uint32_t* bits, size_t n_bits, uint32_t* result_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGPU_H */
