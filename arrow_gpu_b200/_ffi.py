@@ -37,6 +37,7 @@ SIGNATURES = {
     "agpu_free": (_i, [_p, _p]),
     "agpu_h2d": (_i, [_p, _p, _p, _sz]),
     "agpu_d2h": (_i, [_p, _p, _p, _sz]),
+    "agpu_d2h_async": (_i, [_p, _p, _p, _sz]),
     "agpu_d2d": (_i, [_p, _p, _p, _sz]),
     "agpu_memset": (_i, [_p, _p, _i, _sz]),
     "agpu_sync": (_i, [_p]),

@@ -87,16 +87,40 @@ class GpuDevice:
         check(lib().agpu_alloc(self.handle, _round_up(max(size, 1), 16), C.byref(p)), "agpu_alloc")
         return ArrowGpuBuffer(self, p.value, size)
 
-    def create_gpu_buffer_with_data(self, data: np.ndarray) -> "ArrowGpuBuffer":
-        """gpu_device.rs:171-181"""
+    def create_gpu_buffer_with_data(self, data: np.ndarray, wait: bool = True) -> "ArrowGpuBuffer":
+        """gpu_device.rs:171-181.  `wait=False` is for pinned host arrays the caller keeps alive
+        (see `pinned_empty`): the copy is then fully asynchronous on the device's stream."""
         data = np.ascontiguousarray(data)
         buf = self.create_empty_buffer(data.nbytes)
         if data.nbytes:
             check(lib().agpu_h2d(self.handle, buf.ptr, data.ctypes.data, data.nbytes), "agpu_h2d")
-            # the host array may be a temporary: wait so it can be dropped (pageable copies
-            # are staged synchronously by the driver anyway)
-            check(lib().agpu_sync(self.handle), "agpu_sync")
+            if wait:
+                # the host array may be a temporary: wait so it can be dropped (pageable copies
+                # are staged synchronously by the driver anyway)
+                check(lib().agpu_sync(self.handle), "agpu_sync")
         return buf
+
+    @staticmethod
+    def pinned_empty(n: int, dtype) -> np.ndarray:
+        """page-locked host array for from_numpy(..., wait=False) / raw_values(out=...)"""
+        dt = np.dtype(dtype)
+        p = C.c_void_p()
+        check(lib().agpu_host_alloc(max(n * dt.itemsize, 1), C.byref(p)), "agpu_host_alloc")
+        raw = (C.c_uint8 * max(n * dt.itemsize, 1)).from_address(p.value)
+        arr = np.frombuffer(raw, dtype=dt, count=n)
+        _PINNED[arr.ctypes.data] = (p.value, raw)   # keep the mapping alive; freed by pinned_free
+        return arr
+
+    @staticmethod
+    def pinned_free(arr: np.ndarray) -> None:
+        ent = _PINNED.pop(arr.ctypes.data, None)
+        if ent:
+            lib().agpu_host_free(ent[0])
+
+    def read_into(self, buffer: "ArrowGpuBuffer", out: np.ndarray, wait: bool = True) -> None:
+        """device -> caller-provided (ideally pinned) host array"""
+        fn = lib().agpu_d2h if wait else lib().agpu_d2h_async
+        check(fn(self.handle, out.ctypes.data, buffer.ptr, out.nbytes), "agpu_d2h")
 
     def create_scalar_buffer(self, value) -> "ArrowGpuBuffer":
         """gpu_device.rs:203-210"""
@@ -166,6 +190,7 @@ class ArrowComputePipeline:
         self.finished = True
 
 
+_PINNED: dict = {}
 _GPU_DEVICE: Optional[GpuDevice] = None
 
 
@@ -335,20 +360,24 @@ class PrimitiveArrayGpu:
         return cls(gpu_device.create_gpu_buffer_with_data(dense), gpu_device, len(value), nb)
 
     @classmethod
-    def from_numpy(cls, values: np.ndarray, valid: Optional[np.ndarray], gpu_device: GpuDevice):
+    def from_numpy(cls, values: np.ndarray, valid: Optional[np.ndarray], gpu_device: GpuDevice, wait: bool = True):
         """bulk constructor: dense values + optional bool validity flags"""
         nb = NullBitBufferGpu.from_flags(gpu_device, valid) if valid is not None else None
         arr = np.ascontiguousarray(values.astype(cls.NP, copy=False))
-        return cls(gpu_device.create_gpu_buffer_with_data(arr), gpu_device, len(arr), nb)
+        return cls(gpu_device.create_gpu_buffer_with_data(arr, wait), gpu_device, len(arr), nb)
 
     @classmethod
     def empty(cls, length: int, gpu_device: GpuDevice, null_buffer=None):
         return cls(gpu_device.create_empty_buffer(length * cls.NP.itemsize), gpu_device, length, null_buffer)
 
     # --- readback
-    def raw_values(self) -> np.ndarray:
+    def raw_values(self, out: Optional[np.ndarray] = None, wait: bool = True) -> np.ndarray:
+        """primitive_array_gpu.rs:70-74; `out` = caller-provided (pinned) host array"""
+        if out is not None:
+            self.gpu_device.read_into(self.data, out[: self.len], wait)
+            return out
         raw = self.gpu_device.retrive_data(self.data, self.len * self.NP.itemsize)
-        return raw.view(self.NP)[: self.len].copy()
+        return raw.view(self.NP)[: self.len]
 
     def values(self) -> list:
         raw = self.raw_values()

@@ -106,6 +106,14 @@ extern "C" int agpu_d2h(agpu_device* dev, void* dst, const void* src, size_t byt
   return 0;
 }
 
+extern "C" int agpu_d2h_async(agpu_device* dev, void* dst, const void* src, size_t bytes) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (bytes == 0) return 0;
+  AGPU_REQUIRE(dst && src);
+  AGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream));
+  return 0;
+}
+
 extern "C" int agpu_d2d(agpu_device* dev, void* dst, const void* src, size_t bytes) {
   if (!dev) return AGPU_ENODEVICE;
   if (bytes == 0) return 0;

@@ -15,12 +15,15 @@ struct BmMerge {
   const uint32_t *va, *vb, *mask, *vmask;
   uint32_t* out;
   int vec;
+  size_t last_word;     // word holding row n-1: its padding bits are cleared
+  uint32_t last_mask;
   __device__ __forceinline__ uint32_t word(size_t w) const {
     const uint32_t m = mask[w];
     const uint32_t a = va ? va[w] : 0xFFFFFFFFu;
     const uint32_t b = vb ? vb[w] : 0xFFFFFFFFu;
     const uint32_t vm = vmask ? vmask[w] : 0xFFFFFFFFu;
-    return ((a & m) | (b & ~m)) & vm;
+    const uint32_t r = ((a & m) | (b & ~m)) & vm;
+    return w == last_word ? (r & last_mask) : r;
   }
   __device__ __forceinline__ void tile(size_t w0, int tile_words, size_t nwords) const {
     if (!out) return;
@@ -393,7 +396,7 @@ extern "C" int agpu_merge(agpu_device* dev, int dtype, const void* a, const void
   if (n && (!a || !b || !mask || !out)) return AGPU_EINVAL;
   if (vout && !va && !vb && !vmask) return AGPU_EINVAL;
   if (n == 0) return 0;
-  BmMerge bm{va, vb, mask, vmask, vout, 0};
+  BmMerge bm{va, vb, mask, vmask, vout, 0, (n - 1) >> 5, (n & 31) ? ((1u << (n & 31)) - 1u) : 0xFFFFFFFFu};
   if (dtype == AGPU_BOOL) {
     const size_t nwords = (n + 31) / 32;
     BoolMergeOp op{(const uint32_t*)a, (const uint32_t*)b, mask, (uint32_t*)out, bm, nwords - 1,

@@ -125,6 +125,8 @@ int agpu_free(agpu_device* dev, void* ptr);
 int agpu_h2d(agpu_device* dev, void* dst_dev, const void* src_host, size_t bytes);
 /* retrive_data, gpu_device.rs:232-265 — copies and waits for the stream */
 int agpu_d2h(agpu_device* dev, void* dst_host, const void* src_dev, size_t bytes);
+/* same copy without the wait (dst_host should be pinned); ordered on the handle's stream */
+int agpu_d2h_async(agpu_device* dev, void* dst_host, const void* src_dev, size_t bytes);
 /* clone_buffer / copy_buffer_to_buffer, gpu_device.rs:212-230, compute_pipeline.rs:275-300 */
 int agpu_d2d(agpu_device* dev, void* dst_dev, const void* src_dev, size_t bytes);
 int agpu_memset(agpu_device* dev, void* dst_dev, int byte_value, size_t bytes);

@@ -189,6 +189,21 @@ def assert_values(got, expected, *, float_tol: bool, what: str):
             assert g == e, f"{what}[{i}]: {g!r} != {e!r}\n got {got}\n exp {expected}"
 
 
+def same_f32_bits(got, want) -> bool:
+    """bit-for-bit equality of two f32 arrays, except that any NaN equals any NaN: IEEE 754 and
+    WGSL leave NaN sign/payload unspecified (x86 SSE produces 0xFFC00000 for invalid operations
+    and propagates input payloads, sm_100 produces the canonical 0x7FFFFFFF), and the reference's
+    own float comparator treats NaN == NaN (crates/test_macros/src/lib.rs:89-94)."""
+    g = np.ascontiguousarray(got, dtype=np.float32)
+    w = np.ascontiguousarray(want, dtype=np.float32)
+    if g.shape != w.shape:
+        return False
+    gn, wn = np.isnan(g), np.isnan(w)
+    if not np.array_equal(gn, wn):
+        return False
+    return bool(np.array_equal(g.view(np.uint32)[~gn], w.view(np.uint32)[~wn]))
+
+
 def ulp_diff(got: np.ndarray, ref: np.ndarray) -> np.ndarray:
     """distance in f32 ULPs; NaN vs NaN and equal infinities count as 0"""
     g = np.asarray(got, dtype=np.float32)

@@ -1,0 +1,344 @@
+"""GPU: randomized bit-parity of every (op, dtype) against the oracle on the same seeded inputs,
+at ragged sizes (0, 1, word/tile boundaries +-1, > one tile), with and without nulls and through
+unaligned views; ULP bounds for f32 transcendentals; size-independent properties at large N."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import arrow_gpu_b200 as ag
+from arrow_gpu_b200 import kernels as K
+from arrow_gpu_b200 import _ffi
+import oracle as O
+from helpers import OArr, oracle_binary, oracle_cast, oracle_scalar, oracle_unary, same_f32_bits, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+INT_CLS = {O.I8: ag.Int8ArrayGPU, O.U8: ag.UInt8ArrayGPU, O.I16: ag.Int16ArrayGPU, O.U16: ag.UInt16ArrayGPU,
+           O.I32: ag.Int32ArrayGPU, O.U32: ag.UInt32ArrayGPU}
+ALL_CLS = dict(INT_CLS)
+ALL_CLS[O.F32] = ag.Float32ArrayGPU
+ALL_CLS[O.DATE32] = ag.Date32ArrayGPU
+NAMES = {O.I8: "i8", O.U8: "u8", O.I16: "i16", O.U16: "u16", O.I32: "i32", O.U32: "u32", O.F32: "f32", O.DATE32: "date32"}
+SIZES = [0, 1, 3, 31, 32, 33, 127, 1000, 4096, 16384 + 5, 70001]
+
+
+def rand_vals(rng, dtype, n, special=True):
+    if dtype == O.F32:
+        x = rng.uniform(-1000, 1000, n).astype(np.float32)
+        if special and n >= 8:
+            x[:8] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-40, -1e-40, 3.4e38]
+        return x
+    info = np.iinfo(O.NP[dtype])
+    x = rng.integers(info.min, int(info.max) + 1, n, dtype=np.int64).astype(O.NP[dtype])
+    if special and n >= 6:
+        x[:6] = np.array([0, 1, -1 if info.min < 0 else info.max, info.min, info.max, 2]).astype(O.NP[dtype])
+    return x
+
+
+def make(rng, dtype, n, nulls, device, vals=None):
+    vals = rand_vals(rng, dtype, n) if vals is None else vals
+    valid = rng.random(n) < 0.85 if nulls else None
+    g = ALL_CLS[dtype].from_numpy(vals, valid, device)
+    o = OArr(dtype, vals.copy(), n, O.pack_bits(valid) if nulls else None)
+    return g, o
+
+
+def assert_same(g, o: OArr, what):
+    assert g.len == o.n, what
+    gv, ov = g.raw_values(), o.raw_values()
+    if gv.dtype == np.float32:
+        assert same_f32_bits(gv, ov), what
+    else:
+        assert np.array_equal(gv, ov), what
+    if o.valid is None:
+        assert g.null_buffer is None, what
+    else:
+        # whole words must match: padding bits are zero on both sides
+        raw = g.gpu_device.retrive_data(g.null_buffer.bit_buffer, O.words(o.n) * 4).view(np.uint32)
+        assert np.array_equal(raw, o.valid), what + " (validity)"
+
+
+BIN_INT = ["add", "sub", "mul", "div", "min", "max", "bitwise_and", "bitwise_or", "bitwise_xor"]
+OPS_NEW_SURFACE = {"div"}  # array/array int div is not a reference method name: use the C ABI id
+
+
+@pytest.mark.parametrize("dtype", list(INT_CLS), ids=lambda d: NAMES[d])
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "min", "max", "bitwise_and", "bitwise_or", "bitwise_xor"])
+def test_int_binary(op, dtype, device):
+    rng = np.random.default_rng(hash((op, dtype)) % 2**32)
+    for n in SIZES:
+        for nulls in (False, True):
+            a, oa = make(rng, dtype, n, nulls, device)
+            b, ob = make(rng, dtype, n, nulls and n % 2 == 0, device)
+            assert_same(getattr(a, op)(b), oracle_binary(op, oa, ob), f"{op} {NAMES[dtype]} n={n} nulls={nulls}")
+
+
+@pytest.mark.parametrize("dtype", list(INT_CLS) + [O.F32], ids=lambda d: NAMES[d])
+@pytest.mark.parametrize("op", ["add_scalar", "sub_scalar", "mul_scalar", "div_scalar", "rem_scalar"])
+def test_scalar(op, dtype, device):
+    rng = np.random.default_rng(hash((op, dtype)) % 2**32)
+    scalars = [3, 0, 1] if dtype != O.F32 else [3.5, 0.0, -0.25]
+    if np.dtype(O.NP[dtype]).kind == "i":
+        scalars.append(-1)  # MIN / -1 and MIN % -1
+    for n in (0, 5, 1000, 70001):
+        for s in scalars:
+            a, oa = make(rng, dtype, n, n % 2 == 1, device)
+            sc = ALL_CLS[dtype].from_slice([s], device)
+            want = oracle_scalar(op, oa, OArr.from_slice(dtype, [s]))
+            assert_same(getattr(a, op)(sc), want, f"{op} {NAMES[dtype]} n={n} s={s}")
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div", "min", "max"])
+def test_f32_binary(op, device):
+    rng = np.random.default_rng(7)
+    for n in SIZES:
+        a, oa = make(rng, O.F32, n, True, device)
+        b, ob = make(rng, O.F32, n, False, device)
+        if n >= 16:  # 0/0, x/0, -0 vs +0 for min/max, NaN pairs
+            ob.data[:16] = [0.0, 0.0, np.nan, -0.0, 0.0, 5.0, np.inf, -np.inf, 0.0, -0.0, np.nan, 1.0, 2.0, 0.0, 0.0, 0.0]
+            oa.data[8:16] = [-0.0, 0.0, np.nan, np.nan, 0.0, 1.0, -1.0, np.inf]
+            a = ag.Float32ArrayGPU.from_numpy(oa.data, O.unpack_bits(oa.valid, n), device)
+            b = ag.Float32ArrayGPU.from_numpy(ob.data, None, device)
+        assert_same(getattr(a, op)(b), oracle_binary(op, oa, ob), f"{op} f32 n={n}")
+
+
+@pytest.mark.parametrize("dtype", list(ALL_CLS), ids=lambda d: NAMES[d])
+@pytest.mark.parametrize("op", ["gt", "gteq", "lt", "lteq", "eq"])
+def test_compare(op, dtype, device):
+    rng = np.random.default_rng(hash((op, dtype)) % 2**32)
+    for n in SIZES:
+        a, oa = make(rng, dtype, n, True, device)
+        b, ob = make(rng, dtype, n, n % 2 == 0, device)
+        if n > 20:  # force equal pairs
+            ob.data[10:20] = oa.data[10:20]
+            b = ALL_CLS[dtype].from_numpy(ob.data, None if ob.valid is None else O.unpack_bits(ob.valid, n), device)
+        got = getattr(a, op)(b)
+        want = oracle_binary(op, oa, ob)
+        raw = device.retrive_data(got.data, O.words(n) * 4).view(np.uint32)
+        assert np.array_equal(raw, want.data), f"{op} {NAMES[dtype]} n={n}"   # whole words: padding bits zero
+        assert np.array_equal(got.null_buffer.flags(), O.unpack_bits(want.valid, n))
+
+
+@pytest.mark.parametrize("dtype", list(INT_CLS), ids=lambda d: NAMES[d])
+@pytest.mark.parametrize("op", ["bitwise_shl", "bitwise_shr"])
+def test_shift(op, dtype, device):
+    rng = np.random.default_rng(hash((op, dtype)) % 2**32)
+    width = O.NP[dtype].itemsize * 8
+    for n in SIZES:
+        a, oa = make(rng, dtype, n, True, device)
+        counts = rng.integers(0, width, n).astype(np.uint32)
+        if n > 40:  # counts >= width and >= 32: WGSL takes the count mod 32 on the widened lane (Q17)
+            counts[20:30] = rng.integers(width, 64, 10)
+            if dtype == O.I16:  # the i16 shr helper is unpinned for counts >= 16: keep shl only there
+                if op == "bitwise_shr":
+                    counts[20:30] = rng.integers(0, 16, 10)
+        c = ag.UInt32ArrayGPU.from_numpy(counts, None, device)
+        oc = OArr(O.U32, counts, n)
+        assert_same(getattr(a, op)(c), oracle_binary(op, oa, oc), f"{op} {NAMES[dtype]} n={n}")
+
+
+@pytest.mark.parametrize("dtype", list(INT_CLS), ids=lambda d: NAMES[d])
+def test_not(dtype, device):
+    rng = np.random.default_rng(dtype)
+    for n in SIZES:
+        a, oa = make(rng, dtype, n, n % 2 == 1, device)
+        assert_same(a.bitwise_not(), oracle_unary("bitwise_not", oa), f"not {NAMES[dtype]} n={n}")
+
+
+CASTS = [(O.I8, O.U8), (O.I8, O.U16), (O.I8, O.U32), (O.I8, O.I16), (O.I8, O.I32), (O.I8, O.F32),
+         (O.I16, O.I32), (O.I16, O.U16), (O.I16, O.U32), (O.I16, O.F32),
+         (O.U8, O.U16), (O.U8, O.U32), (O.U8, O.I8), (O.U8, O.I16), (O.U8, O.I32), (O.U8, O.F32),
+         (O.U16, O.U32), (O.U16, O.I16), (O.U16, O.I32), (O.U16, O.F32), (O.F32, O.U8)]
+
+
+@pytest.mark.parametrize("pair", CASTS, ids=lambda p: f"{NAMES[p[0]]}->{NAMES[p[1]]}")
+def test_cast(pair, device):
+    src, dst = pair
+    rng = np.random.default_rng(src * 16 + dst)
+    for n in SIZES:
+        vals = None
+        if src == O.F32:
+            vals = rng.uniform(-10, 70000, n).astype(np.float32)
+            if n >= 8:
+                vals[:8] = [0.0, -0.0, -1.0, 255.0, 256.0, np.nan, np.inf, 5e9]
+        a, oa = make(rng, src, n, n % 2 == 1, device, vals)
+        assert_same(a.cast(ALL_CLS[dst]), oracle_cast(oa, dst), f"cast n={n}")
+
+
+def test_cast_bool_to_f32_and_bitcast(device):
+    rng = np.random.default_rng(3)
+    for n in SIZES:
+        flags = rng.random(n) < 0.5
+        valid = rng.random(n) < 0.9
+        b = ag.BooleanArrayGPU.from_numpy(flags, valid, device)
+        want = oracle_cast(OArr(O.BOOL, O.pack_bits(flags), n, O.pack_bits(valid)), O.F32)
+        assert_same(b.cast(ag.Float32ArrayGPU), want, f"bool->f32 n={n}")
+        u = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+        g = ag.UInt32ArrayGPU.from_numpy(u, None, device).bitcast(ag.Float32ArrayGPU)
+        assert np.array_equal(g.raw_values().view(np.uint32), u)
+
+
+def test_bool_logical(device):
+    rng = np.random.default_rng(5)
+    for n in SIZES:
+        fa, fb = rng.random(n) < 0.5, rng.random(n) < 0.5
+        va, vb = rng.random(n) < 0.9, rng.random(n) < 0.9
+        a = ag.BooleanArrayGPU.from_numpy(fa, va, device)
+        b = ag.BooleanArrayGPU.from_numpy(fb, vb, device)
+        oa = OArr(O.BOOL, O.pack_bits(fa), n, O.pack_bits(va))
+        ob = OArr(O.BOOL, O.pack_bits(fb), n, O.pack_bits(vb))
+        for op in ("bitwise_and", "bitwise_or", "bitwise_xor"):
+            got, want = getattr(a, op)(b), oracle_binary(op, oa, ob)
+            assert np.array_equal(device.retrive_data(got.data, O.words(n) * 4).view(np.uint32), want.data), (op, n)
+            assert np.array_equal(got.null_buffer.flags(), O.unpack_bits(want.valid, n))
+        got, want = a.bitwise_not(), oracle_unary("bitwise_not", oa)
+        assert np.array_equal(device.retrive_data(got.data, O.words(n) * 4).view(np.uint32), want.data), ("not", n)
+
+
+def test_i32_abs_power_neg(device):
+    rng = np.random.default_rng(11)
+    n = 5000
+    x = rng.integers(-50, 50, n).astype(np.int32)
+    p = rng.integers(-6, 12, n).astype(np.int32)
+    x[:4] = [np.iinfo(np.int32).min, 0, -1, 1]
+    p[:4] = [1, -3, -5, -7]
+    a, b = ag.Int32ArrayGPU.from_numpy(x, None, device), ag.Int32ArrayGPU.from_numpy(p, None, device)
+    assert np.array_equal(a.power(b).raw_values(), O.binary(O.POW, O.I32, x, p))
+    assert np.array_equal(a.abs().raw_values(), O.unary(O.ABS, O.I32, x))
+    f = rand_vals(rng, O.F32, n)
+    assert same_f32_bits(ag.Float32ArrayGPU.from_numpy(f, None, device).neg().raw_values(), O.unary(O.NEG, O.F32, f))
+
+
+# ---- f32 transcendentals: stated ULP bounds against the correctly rounded value -------------
+# (op, input range, max ULP).  sqrt/abs/neg must be exact.  Bounds are the documented CUDA libm
+# bounds (CUDA C Programming Guide, "Mathematical Functions"): sinf/cosf 2, expf/exp2f 2, logf 1,
+# log2f 1, powf 4 (cbrt goes through powf like the reference), sinhf 3, acosf 2.
+ULP_CASES = [("sqrt", (0, 1e6), 0), ("exp", (-20, 20), 2), ("exp2", (-30, 30), 2), ("log", (1e-6, 1e6), 1),
+             ("log2", (1e-6, 1e6), 1), ("sin", (-100, 100), 2), ("cos", (-100, 100), 2), ("acos", (-1, 1), 2),
+             ("sinh", (-10, 10), 3), ("cbrt", (-1e6, 1e6), 4), ("abs", (-1e6, 1e6), 0)]
+
+
+@pytest.mark.parametrize("op,rng_,bound", ULP_CASES, ids=[c[0] for c in ULP_CASES])
+def test_f32_math_ulp(op, rng_, bound, device):
+    rng = np.random.default_rng(30)
+    n = 1 << 20
+    x = rng.uniform(rng_[0], rng_[1], n).astype(np.float32)
+    got = getattr(ag.Float32ArrayGPU.from_numpy(x, None, device), op)().raw_values()
+    want = oracle_unary(op, OArr(O.F32, x, n)).raw_values()
+    d = ulp_diff(got, want)
+    assert d.max() <= bound, f"{op}: max {d.max()} ULP at x={x[d.argmax()]!r} got {got[d.argmax()]!r} want {want[d.argmax()]!r}"
+
+
+def test_f32_math_special_values(device):
+    x = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, -1.0, 1.0, 1e-45, 3e38], np.float32)
+    a = ag.Float32ArrayGPU.from_numpy(x, None, device)
+    for op in ("sqrt", "exp", "exp2", "log", "log2", "sin", "cos", "acos", "sinh", "cbrt"):
+        got = getattr(a, op)().raw_values()
+        want = oracle_unary(op, OArr(O.F32, x, len(x))).raw_values()
+        with np.errstate(all="ignore"):
+            assert np.array_equal(np.isnan(got), np.isnan(want)), (op, got, want)
+            assert np.array_equal(np.isinf(got), np.isinf(want)), (op, got, want)
+            fin = np.isfinite(want)
+            assert ulp_diff(got[fin], want[fin]).max(initial=0) <= 4, (op, got, want)
+
+
+def test_f32_power_ulp(device):
+    rng = np.random.default_rng(31)
+    n = 1 << 18
+    x = rng.uniform(0, 50, n).astype(np.float32)
+    y = rng.uniform(-4, 4, n).astype(np.float32)
+    got = ag.Float32ArrayGPU.from_numpy(x, None, device).power(ag.Float32ArrayGPU.from_numpy(y, None, device)).raw_values()
+    want = O.binary(O.POW, O.F32, x, y)
+    assert ulp_diff(got, want).max() <= 4
+
+
+@pytest.mark.parametrize("dtype", [O.I8, O.U8, O.I16, O.U16], ids=lambda d: NAMES[d])
+def test_int_trig_fused_cast(dtype, device):
+    """trigonometry/compute_shaders/{i8,u8,i16,u16}: cast to f32 fused with sin/cos/sinh"""
+    rng = np.random.default_rng(dtype)
+    n = 50001
+    vals = rand_vals(rng, dtype, n)
+    a, oa = make(rng, dtype, n, True, device, vals)
+    for op, bound in (("sin", 2), ("cos", 2), ("sinh", 3)):
+        got = getattr(a, op)()
+        assert type(got) is ag.Float32ArrayGPU
+        want = oracle_unary(op, oa)
+        d = ulp_diff(got.raw_values(), want.raw_values())
+        # |x| up to 65535 leaves CUDA's fast sinf/cosf path above 105615 only; still 2 ULP
+        assert d.max() <= bound, (op, NAMES[dtype], d.max())
+        assert np.array_equal(got.null_buffer.flags(), O.unpack_bits(want.valid, n))
+
+
+# ---- unaligned device pointers: same results through the element-wise fallback kernels ----------
+def test_unaligned_pointers(device):
+    l = _ffi.lib()
+    rng = np.random.default_rng(9)
+    n = 10007
+    for dtype in (O.I8, O.I16, O.F32):
+        es = O.NP[dtype].itemsize
+        x, y = rand_vals(rng, dtype, n + 4), rand_vals(rng, dtype, n + 4)
+        bx, by = device.create_gpu_buffer_with_data(x), device.create_gpu_buffer_with_data(y)
+        out = device.create_empty_buffer((n + 4) * es)
+        bits = device.create_empty_buffer(O.words(n) * 4)
+        off = es  # one element: breaks 16-byte alignment
+        _ffi.check(l.agpu_binary(device.handle, O.ADD, dtype, bx.ptr + off, by.ptr + off, out.ptr + off, n,
+                                 None, None, None), "binary")
+        got = device.retrive_data(out, (n + 4) * es).view(O.NP[dtype])[1:n + 1]
+        want = O.binary(O.ADD, dtype, x[1:n + 1], y[1:n + 1])
+        assert same_f32_bits(got, want) if dtype == O.F32 else np.array_equal(got, want)
+        _ffi.check(l.agpu_compare(device.handle, O.GT, dtype, bx.ptr + off, by.ptr + off, bits.ptr, n,
+                                  None, None, None), "compare")
+        assert np.array_equal(device.retrive_data(bits, O.words(n) * 4).view(np.uint32),
+                              O.compare(O.GT, dtype, x[1:n + 1], y[1:n + 1]))
+
+
+# ---- fused expression == unfused reference chain, bit for bit ----------------------------------
+def test_fused_mul_add_gt(device):
+    rng = np.random.default_rng(20)
+    for n in SIZES + [1 << 20]:
+        cols, ocols = [], []
+        for k in range(4):
+            g, o = make(rng, O.F32, n, k != 2, device, rng.uniform(-10, 10, n).astype(np.float32))
+            cols.append(g)
+            ocols.append(o)
+        fused = K.fused_mul_add_gt(*cols)
+        pipeline = ag.ArrowComputePipeline(device, "chain")
+        chain = K.gt_op_dyn(K.add_op_dyn(K.mul_op_dyn(cols[0], cols[1], pipeline), cols[2], pipeline), cols[3], pipeline)
+        pipeline.finish()
+        want = oracle_binary("gt", oracle_binary("add", oracle_binary("mul", ocols[0], ocols[1]), ocols[2]), ocols[3])
+        for got in (fused, chain):
+            assert np.array_equal(device.retrive_data(got.data, O.words(n) * 4).view(np.uint32), want.data), n
+            assert np.array_equal(device.retrive_data(got.null_buffer.bit_buffer, O.words(n) * 4).view(np.uint32),
+                                  want.valid), n
+
+
+# ---- sum: same tree order as the reference => bit-identical f32 result ---------------------------
+def test_sum_bit_exact(device):
+    rng = np.random.default_rng(40)
+    for n in (1, 255, 256, 257, 65536, 65537, 1_000_003, 5_000_000):
+        x = rng.uniform(-1000, 1000, n).astype(np.float32)
+        got = ag.Float32ArrayGPU.from_numpy(x, None, device).sum().raw_values()[0]
+        assert np.float32(got).view(np.uint32) == np.float32(O.sum(O.F32, x)).view(np.uint32), n
+        i = rng.integers(-2**31, 2**31, n).astype(np.int32)
+        assert ag.Int32ArrayGPU.from_numpy(i, None, device).sum().raw_values()[0] == O.sum(O.I32, i)
+
+
+# ---- size-independent properties at BASELINE.json scale (256 Mi rows of i8) -----------------------
+def test_large_properties_i8(device):
+    n = 1 << 28
+    rng = np.random.default_rng(10)
+    x = rng.integers(-128, 128, n, dtype=np.int8)
+    y = rng.integers(-128, 128, n, dtype=np.int8)
+    a, b = ag.Int8ArrayGPU.from_numpy(x, None, device), ag.Int8ArrayGPU.from_numpy(y, None, device)
+    # (a + b) - b == a under wrap-around; xor is an involution; gt/lteq are complementary
+    assert np.array_equal(a.add(b).sub(b).raw_values(), x)
+    assert np.array_equal(a.bitwise_xor(b).bitwise_xor(b).raw_values(), x)
+    gt, le = a.gt(b), a.lteq(b)
+    assert gt.bitwise_xor(le).all() is True
+    assert gt.bitwise_and(le).any() is False
+    # checksum of the sum against numpy on a strided sample + exact count of a > b
+    s = a.add(b).raw_values()
+    idx = np.arange(0, n, 9973)
+    assert np.array_equal(s[idx], (x[idx].astype(np.int16) + y[idx]).astype(np.int8))
+    assert int(gt.raw_values().sum()) == int((x > y).sum())
