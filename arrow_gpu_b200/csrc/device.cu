@@ -1,6 +1,7 @@
 // device.cu — device handle, stream-ordered buffers, copies, events (replaces the reference's
 // GpuDevice: crates/array/src/gpu_utils/gpu_device.rs).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -42,6 +43,12 @@ extern "C" int agpu_device_create(int ordinal, agpu_device** out) {
   unsigned long long threshold = ~0ull;
   cudaMemPoolSetAttribute(d->pool, cudaMemPoolAttrReleaseThreshold, &threshold);
   cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, ordinal);
+  // experiment knob: L2 -> DRAM fetch granularity hint in bytes (32/64/128); gathers fetch less
+  // with a small value, streaming kernels request whole lines either way
+  if (const char* g = getenv("AGPU_L2_FETCH_GRANULARITY")) {
+    const size_t v = (size_t)atoi(g);
+    if (v) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, v);
+  }
   *out = d;
   return 0;
 }

@@ -88,6 +88,18 @@ int run_merge(agpu_device* dev, const void* a, const void* b, const uint32_t* ma
 // take: routines/compute_shaders/32bit/take.wgsl:13-17, bool/take.wgsl:13-33
 // ============================================================================================
 // granule = 4 output rows: one 16-byte chunk of indices per lane, 4 gathers, one chunk store.
+// Gathers go through the read-only path without L1 allocation and ask L2 for the smallest fill
+// it offers (64 bytes instead of the default 128): a random 4-byte gather otherwise drags a whole
+// 128-byte line out of HBM.
+template <typename U>
+__device__ __forceinline__ U ld_gather(const U* p) {
+  uint32_t r;
+  if constexpr (sizeof(U) == 4) asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b32 %0, [%1];" : "=r"(r) : "l"(p));
+  else if constexpr (sizeof(U) == 2) asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u16 %0, [%1];" : "=r"(r) : "l"(p));
+  else asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return (U)r;
+}
+
 template <typename U>
 struct TakeOp {
   static constexpr int G = 4;
@@ -96,7 +108,7 @@ struct TakeOp {
   const uint32_t* idx;
   U* out;
   struct In { Vec<uint32_t, 4> i; };
-  __device__ __forceinline__ U fetch(uint32_t i) const { return i < src_len ? __ldg(src + i) : (U)0; }
+  __device__ __forceinline__ U fetch(uint32_t i) const { return i < src_len ? ld_gather<U>(src + i) : (U)0; }
   __device__ __forceinline__ In load(size_t g) const { return In{ld_vec<uint32_t, 4>(idx, g)}; }
   __device__ __forceinline__ void run(size_t g, const In& in) const {
     Vec<U, 4> o;
@@ -184,27 +196,32 @@ __global__ void __launch_bounds__(kBlock) put_bits_kernel(const uint32_t* __rest
 // ============================================================================================
 // filter (compaction)
 // ============================================================================================
-// Tile = 4096 rows = 128 mask words.  Pass 1 (count): one warp per tile, each lane popcounts a
-// 16-byte chunk of (mask & vmask); tile counts go to scratch, the grand total to *total.
-// Pass 2 (scan): exclusive scan of the tile counts -> 64-bit output offsets.
-// Pass 3 (scatter): one CTA per tile.  Warp 0 scans the popcounts of the tile's 128 selection
-// words with shuffles; every thread then loads its rows as coalesced 16-byte granules, finds a
-// selected row's slot as  word_prefix + popc(selection bits below it)  and drops the value into a
-// shared-memory stage, which the CTA finally streams out as contiguous stores.
+// Tile = 4096 rows = 128 mask words; group = 64 tiles.
+// Pass 1 (count): one CTA per group, one warp per 8 tiles; each lane popcounts a 16-byte chunk of
+//   (mask & vmask) per tile (all 8 loads in flight first), a shuffle reduce gives the tile count;
+//   the CTA adds its 64 tile counts into one group total.  No atomics.  Traffic: N/8 bytes.
+// Pass 2 (scan): one CTA scans the group totals (N / 262144 values) -> 64-bit group offsets + the
+//   grand total.  Both run inside agpu_filter_count so the caller can size the output.
+// Pass 3 (scatter): one CTA per tile.  Warp 0 prefix-sums the popcounts of the tile's 128
+//   selection words and adds the counts of the preceding tiles of its group to the group offset.
+//   Every thread loads its rows as coalesced 16-byte granules, a selected row's slot is
+//   word_prefix + popc(selection bits below it); values are staged in shared memory shifted by
+//   (output offset mod G) so that the CTA can stream them out as aligned 16-byte vectors.
 constexpr int kFilterTileRows = 4096;
 constexpr int kFilterTileWords = kFilterTileRows / 32;
+constexpr int kFilterGroupTiles = 64;
 
 struct FilterScratch {
-  uint32_t* counts;   // [tiles]
-  uint64_t* offsets;  // [tiles]
+  uint64_t* group_offsets;  // [groups]
+  uint32_t* counts;         // [tiles]
 };
 
 inline size_t filter_tiles(size_t n) { return ceil_div(n, (size_t)kFilterTileRows); }
+inline size_t filter_groups(size_t n) { return ceil_div(filter_tiles(n), (size_t)kFilterGroupTiles); }
 inline FilterScratch filter_scratch(void* p, size_t n) {
-  const size_t tiles = filter_tiles(n);
   FilterScratch s;
-  s.offsets = (uint64_t*)p;
-  s.counts = (uint32_t*)((char*)p + ((tiles * 8 + 15) / 16) * 16);
+  s.group_offsets = (uint64_t*)p;
+  s.counts = (uint32_t*)((char*)p + ((filter_groups(n) * 8 + 15) / 16) * 16);
   return s;
 }
 
@@ -220,39 +237,67 @@ __device__ __forceinline__ uint32_t sel_word(const uint32_t* mask, const uint32_
 __global__ void __launch_bounds__(kBlock) filter_count_kernel(const uint32_t* __restrict__ mask,
                                                               const uint32_t* __restrict__ vmask, const size_t n,
                                                               uint32_t* __restrict__ counts,
-                                                              unsigned long long* __restrict__ total) {
+                                                              uint64_t* __restrict__ group_totals, const int vec) {
+  __shared__ uint32_t warp_tot[kBlock / 32];
   const size_t nwords = (n + 31) / 32;
   const size_t tiles = (n + kFilterTileRows - 1) / kFilterTileRows;
-  const size_t tile = (size_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-  if (tile >= tiles) return;
-  const int lane = threadIdx.x & 31;
-  const size_t w0 = tile * kFilterTileWords + (size_t)lane * 4;
-  uint32_t c = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int TPW = kFilterGroupTiles / (kBlock / 32);  // tiles per warp = 8
+  const size_t t0 = (size_t)blockIdx.x * kFilterGroupTiles + (size_t)warp * TPW;
+  uint32_t c[TPW];
+  if (vec && (t0 + TPW) * kFilterTileRows <= n) {  // all 8 tiles full: vector loads, issued up front
+    uint4 m[TPW];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) c += __popc(sel_word(mask, vmask, w0 + k, nwords, n));
+    for (int k = 0; k < TPW; ++k) m[k] = __ldcs(reinterpret_cast<const uint4*>(mask + (t0 + k) * kFilterTileWords) + lane);
+    if (vmask) {
 #pragma unroll
-  for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, off);
-  if (lane == 0) {
-    counts[tile] = c;
-    if (c) atomicAdd(total, (unsigned long long)c);
+      for (int k = 0; k < TPW; ++k) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(vmask + (t0 + k) * kFilterTileWords) + lane);
+        m[k].x &= v.x; m[k].y &= v.y; m[k].z &= v.z; m[k].w &= v.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) c[k] = __popc(m[k].x) + __popc(m[k].y) + __popc(m[k].z) + __popc(m[k].w);
+  } else {
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) {
+      const size_t w0 = (t0 + k) * kFilterTileWords + (size_t)lane * 4;
+      c[k] = 0;
+      for (int j = 0; j < 4; ++j) c[k] += __popc(sel_word(mask, vmask, w0 + j, nwords, n));
+    }
+  }
+  uint32_t wsum = 0;
+#pragma unroll
+  for (int k = 0; k < TPW; ++k) {
+    uint32_t x = c[k];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, off);
+    if (lane == 0 && t0 + k < tiles) counts[t0 + k] = x;
+    wsum += x;
+  }
+  if (lane == 0) warp_tot[warp] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t tot = 0;
+    for (int w = 0; w < kBlock / 32; ++w) tot += warp_tot[w];
+    group_totals[blockIdx.x] = tot;
   }
 }
 
-// single-CTA exclusive scan, 8 tiles per thread per round
-__global__ void __launch_bounds__(1024) filter_scan_kernel(const uint32_t* __restrict__ counts,
-                                                           uint64_t* __restrict__ offsets, const size_t tiles) {
+// single-CTA exclusive scan of the group totals (in place), 8 per thread per round
+__global__ void __launch_bounds__(1024) filter_scan_kernel(uint64_t* __restrict__ groups, const size_t n_groups,
+                                                           unsigned long long* __restrict__ total) {
   __shared__ uint64_t warp_tot[32];
   __shared__ uint64_t carry_s;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (size_t base = 0; base < tiles; base += 1024 * 8) {
-    const size_t t0 = base + (size_t)threadIdx.x * 8;
-    uint32_t c[8];
-    uint64_t sum = 0;
+  for (size_t base = 0; base < n_groups; base += 1024 * 8) {
+    const size_t g0 = base + (size_t)threadIdx.x * 8;
+    uint64_t c[8], sum = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      c[k] = t0 + k < tiles ? counts[t0 + k] : 0u;
+      c[k] = g0 + k < n_groups ? groups[g0 + k] : 0ull;
       sum += c[k];
     }
     uint64_t incl = sum;
@@ -277,13 +322,14 @@ __global__ void __launch_bounds__(1024) filter_scan_kernel(const uint32_t* __res
     uint64_t excl = carry + (incl - sum) + (warp ? warp_tot[warp - 1] : 0);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (t0 + k < tiles) offsets[t0 + k] = excl;
+      if (g0 + k < n_groups) groups[g0 + k] = excl;
       excl += c[k];
     }
     __syncthreads();
     if (threadIdx.x == 0) carry_s = carry + warp_tot[31];
     __syncthreads();
   }
+  if (threadIdx.x == 0) *total = carry_s;
 }
 
 template <typename U, bool HAS_V>
@@ -292,72 +338,111 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restr
                                                                 const uint32_t* __restrict__ mask,
                                                                 const uint32_t* __restrict__ vmask, const size_t n,
                                                                 const uint32_t* __restrict__ counts,
-                                                                const uint64_t* __restrict__ offsets,
+                                                                const uint64_t* __restrict__ group_offsets,
                                                                 U* __restrict__ out, uint32_t* vout) {
   constexpr int G = 16 / sizeof(U);                   // rows per 16-byte granule
   constexpr int GPT = kFilterTileRows / G / kBlock;    // granules per thread
-  __shared__ U stage[kFilterTileRows];
+  __shared__ __align__(16) U stage[kFilterTileRows + G];
   __shared__ uint32_t sel[kFilterTileWords];
   __shared__ uint32_t pre[kFilterTileWords];
-  __shared__ uint32_t vstage[HAS_V ? kFilterTileWords : 1];
+  __shared__ uint32_t vstage[HAS_V ? kFilterTileWords + 1 : 1];
+  __shared__ uint64_t off_s;
+  __shared__ uint32_t count_s;
 
   const size_t tile = blockIdx.x;
-  const uint32_t count = counts[tile];
-  if (count == 0) return;  // uniform for the CTA
   const size_t nwords = (n + 31) / 32;
   const size_t w0 = tile * kFilterTileWords;
   const size_t row0 = tile * kFilterTileRows;
-
-  if (threadIdx.x < kFilterTileWords) {
-    sel[threadIdx.x] = sel_word(mask, vmask, w0 + threadIdx.x, nwords, n);
-    if (HAS_V) vstage[threadIdx.x] = 0u;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {  // exclusive prefix of the 128 popcounts: 4 words per lane
-    const int l = threadIdx.x;
-    uint32_t c[4], s = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { c[k] = __popc(sel[l * 4 + k]); s += c[k]; }
-    uint32_t incl = s;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-      if (l >= off) incl += v;
-    }
-    uint32_t e = incl - s;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { pre[l * 4 + k] = e; e += c[k]; }
-  }
-  __syncthreads();
-
   const bool full = row0 + kFilterTileRows <= n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // everything that comes from global memory is requested up front: the rows (independent of
+  // the selection bits), the selection words, and the counts that place this tile in the output
   Vec<U, G> v[GPT];
   if (full) {
 #pragma unroll
     for (int j = 0; j < GPT; ++j) v[j] = ld_vec<U, G>(src + row0, (size_t)j * kBlock + threadIdx.x);
   }
+  uint32_t before = 0;
+  uint64_t goff = 0;
+  if (warp == 1) {  // warp 1: output offset = group offset + counts of the earlier tiles of the group
+    const size_t gstart = tile / kFilterGroupTiles * kFilterGroupTiles;
+    if (gstart + lane < tile) before += counts[gstart + lane];
+    if (gstart + 32 + lane < tile) before += counts[gstart + 32 + lane];
+    if (lane == 0) goff = group_offsets[tile / kFilterGroupTiles];
+  }
+  if (threadIdx.x < kFilterTileWords) {
+    sel[threadIdx.x] = sel_word(mask, vmask, w0 + threadIdx.x, nwords, n);
+    if (HAS_V) vstage[threadIdx.x] = 0u;
+  }
+  if (HAS_V && threadIdx.x == 0) vstage[kFilterTileWords] = 0u;
+  if (warp == 1) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
+    if (lane == 0) off_s = goff + before;
+  }
+  __syncthreads();
+  if (warp == 0) {  // warp 0: exclusive prefix of the 128 popcounts, 4 words per lane
+    uint32_t c[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c[k] = __popc(sel[lane * 4 + k]); s += c[k]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= off) incl += x;
+    }
+    uint32_t e = incl - s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { pre[lane * 4 + k] = e; e += c[k]; }
+    if (lane == 31) count_s = incl;
+  }
+  __syncthreads();
+  const uint32_t count = count_s;
+  if (count == 0) return;  // uniform for the CTA
+  const uint64_t off = off_s;
+  const bool vec_out = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  const uint32_t lead = vec_out ? (uint32_t)(off % G) : 0u;  // shift so that 16-byte vectors line up
+
 #pragma unroll
   for (int j = 0; j < GPT; ++j) {
     const int r = (j * kBlock + threadIdx.x) * G;  // first row of the granule within the tile
     const uint32_t sw = sel[r >> 5];
-    const uint32_t bits = (sw >> (r & 31)) & ((G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u));
+    const uint32_t bits = (sw >> (r & 31)) & ((1u << G) - 1u);
     if (bits == 0) continue;
-    uint32_t pos = pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
+    uint32_t pos = lead + pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
     uint32_t vw = 0;
     if (HAS_V) vw = vsrc[(row0 + r) >> 5] >> (r & 31);
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       if ((bits >> k) & 1u) {
         stage[pos] = full ? v[j].e[k] : src[row0 + r + k];
-        if (HAS_V && ((vw >> k) & 1u)) atomicOr(&vstage[pos >> 5], 1u << (pos & 31));
+        if (HAS_V && ((vw >> k) & 1u)) atomicOr(&vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
         ++pos;
       }
     }
   }
   __syncthreads();
 
-  const uint64_t off = offsets[tile];
-  for (uint32_t i = threadIdx.x; i < count; i += kBlock) out[off + i] = stage[i];
+  if (vec_out) {
+    // staged elements [lead, lead+count) map to out[off .. off+count); vector q covers staged
+    // elements [q*G, q*G+G) = global elements (off - lead) + q*G .., 16-byte aligned
+    U* gbase = out + (off - lead);
+    const uint32_t end = lead + count;
+    const uint32_t nvec = (end + G - 1) / G;
+    for (uint32_t q = threadIdx.x; q < nvec; q += kBlock) {
+      const uint32_t e0 = q * G;
+      if (e0 >= lead && e0 + G <= end) {
+        Vec<U, G> t = *reinterpret_cast<const Vec<U, G>*>(stage + e0);
+        st_vec<U, G>(gbase, q, t);
+      } else {
+        for (uint32_t k = 0; k < (uint32_t)G; ++k)
+          if (e0 + k >= lead && e0 + k < end) gbase[e0 + k] = stage[e0 + k];
+      }
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < count; i += kBlock) out[off + i] = stage[i];
+  }
   if (HAS_V) {
     const uint32_t lw_n = (count + 31) / 32;
     const uint32_t s = (uint32_t)(off & 31);
@@ -379,10 +464,10 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
   if (vsrc && vout) {
     AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
     AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true>), (unsigned)tiles, kBlock, 0, (const U*)src, vsrc, mask, vmask,
-                n, sc.counts, sc.offsets, (U*)out, vout);
+                n, sc.counts, sc.group_offsets, (U*)out, vout);
   } else {
     AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false>), (unsigned)tiles, kBlock, 0, (const U*)src, vsrc, mask, vmask,
-                n, sc.counts, sc.offsets, (U*)out, vout);
+                n, sc.counts, sc.group_offsets, (U*)out, vout);
   }
   return agpu_finish_launch();
 }
@@ -452,22 +537,23 @@ extern "C" int agpu_put(agpu_device* dev, int dtype, const void* src, const uint
 }
 
 extern "C" size_t agpu_filter_scratch_bytes(size_t n) {
-  const size_t tiles = filter_tiles(n);
-  return ((tiles * 8 + 15) / 16) * 16 + ((tiles * 4 + 15) / 16) * 16 + 16;
+  return ((filter_groups(n) * 8 + 15) / 16) * 16 + ((filter_tiles(n) * 4 + 15) / 16) * 16 + 16;
 }
 
 extern "C" int agpu_filter_count(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n,
                                  void* scratch, uint64_t* total_dev) {
   if (!dev) return AGPU_ENODEVICE;
   if (!scratch || !total_dev || (n && !mask)) return AGPU_EINVAL;
-  AGPU_CUDA(cudaMemsetAsync(total_dev, 0, 8, dev->stream));
-  if (n == 0) return 0;
+  if (n == 0) {
+    AGPU_CUDA(cudaMemsetAsync(total_dev, 0, 8, dev->stream));
+    return 0;
+  }
   const FilterScratch sc = filter_scratch(scratch, n);
-  const size_t tiles = filter_tiles(n);
-  const size_t grid = ceil_div(tiles, (size_t)(kBlock / 32));
-  if (grid > 0x7FFFFFFFull) return AGPU_EINVAL;
-  AGPU_LAUNCH(dev, filter_count_kernel, (unsigned)grid, kBlock, 0, mask, vmask, n, sc.counts,
-              (unsigned long long*)total_dev);
+  const size_t groups = filter_groups(n);
+  if (groups > 0x7FFFFFFFull) return AGPU_EINVAL;
+  const int vec = aligned16(mask) && (!vmask || aligned16(vmask));
+  AGPU_LAUNCH(dev, filter_count_kernel, (unsigned)groups, kBlock, 0, mask, vmask, n, sc.counts, sc.group_offsets, vec);
+  AGPU_LAUNCH(dev, filter_scan_kernel, 1, 1024, 0, sc.group_offsets, groups, (unsigned long long*)total_dev);
   return agpu_finish_launch();
 }
 
@@ -478,9 +564,6 @@ extern "C" int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src,
   if (n && (!src || !mask || !scratch || !out)) return AGPU_EINVAL;
   if (n == 0) return 0;
   const FilterScratch sc = filter_scratch(scratch, n);
-  AGPU_LAUNCH(dev, filter_scan_kernel, 1, 1024, 0, sc.counts, sc.offsets, filter_tiles(n));
-  int rc = agpu_finish_launch();
-  if (rc) return rc;
   switch (agpu_dtype_size(dtype)) {
     case 4: return run_filter<uint32_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
     case 2: return run_filter<uint16_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);

@@ -216,11 +216,13 @@ def run_ours(args, rank, world, local_rank):
             if events is not None:
                 record(events[k + 1])
 
-    for _ in range(args.warmup):
+    # the sampler runs from the warm-up on (same load as the timed steps): the timed region of
+    # K=5 steps lasts ~50 ms, shorter than nvidia-smi's sampling period
+    clocks_proc = sample_clocks_start(local_rank)
+    for _ in range(max(args.warmup, 1) * 8):
         resident_step()
     dev.sync()
     sharded.barrier()
-    clocks_proc = sample_clocks_start(local_rank)
     step_events = [[new_event() for _ in range(len(ops) + 1)] for _ in range(args.steps)]
     launches0 = dev.launch_count()
     t_start, t_stop = new_event(), new_event()
@@ -368,12 +370,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=ROWS_CFG2, help="rows per GPU (default: config 2's 256 Mi)")
+    ap.add_argument("--rows", type=int, default=None, help="rows (default: the workload's own size; cfg2: 256 Mi per GPU)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[k-1]; cfg2 is the bench line, the others are scaling/parity configs")
     ap.add_argument("--cpu-rows", type=int, default=1 << 24, help="rows of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.rows_given = args.rows is not None
+    if args.rows is None:
+        args.rows = ROWS_CFG2
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -391,6 +398,14 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
+        if args.workload != "cfg2":
+            import bench_workloads
+            res = bench_workloads.run(args, rank, world, local_rank,
+                                      {"clocks_start": sample_clocks_start, "clocks_stop": sample_clocks_stop,
+                                       "peak": measured_peak, "traffic": known_traffic})
+            if rank == 0:
+                print(json.dumps(res))
+            return
         res = run_ours(args, rank, world, local_rank)
         if rank == 0:
             if not args.no_cpu_baseline and world == 1:

@@ -1,0 +1,218 @@
+"""The other BASELINE.json configurations (cfg1, cfg3, cfg4, cfg5) for `bench.py --workload`.
+
+These are the parity-test / scaling configurations; the default bench line is config 2 (bench.py).
+Columns of 1-4 G rows are synthesised ON THE DEVICE with torch (seeded generators) — torch is used
+only as an allocator/RNG here; every measured kernel is ours, launched through the C ABI on the
+library's own stream and timed with CUDA events on that stream.  No e2e number is produced for
+these workloads (their inputs never exist on the host), except cfg1.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import statistics
+
+import numpy as np
+
+ROWS = {"cfg1": 1_048_576, "cfg3": 1_000_000_000, "cfg4": 4_000_000_000, "cfg5": 4_000_000_000}
+
+
+def _wrap(ag, cls, tensor, n, dev, keep):
+    """zero-copy: a torch CUDA tensor's memory as one of our arrays (not owned by our pool)"""
+    keep.append(tensor)
+    return cls(ag.ArrowGpuBuffer(dev, tensor.data_ptr(), tensor.numel() * tensor.element_size(), owned=False), dev, n, None)
+
+
+def _bitmap(torch, n, p, seed, device):
+    """Bernoulli(p) bits, LSB-first, as a uint8 tensor padded to whole u32 words"""
+    nbytes = (n + 31) // 32 * 4
+    out = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    weights = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.int32, device=device)
+    chunk = 1 << 28
+    for start in range(0, n, chunk):
+        m = min(chunk, n - start)
+        bits = (torch.rand(m, generator=g, device=device) < p)
+        pad = (-m) % 8
+        if pad:
+            bits = torch.cat([bits, torch.zeros(pad, dtype=torch.bool, device=device)])
+        packed = (bits.view(-1, 8).to(torch.int32) * weights).sum(dim=1).to(torch.uint8)
+        out[start // 8: start // 8 + packed.numel()] = packed
+        del bits, packed
+    return out
+
+
+def _uniform(torch, n, lo, hi, seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    chunk = 1 << 28
+    for start in range(0, n, chunk):
+        m = min(chunk, n - start)
+        out[start:start + m].uniform_(lo, hi, generator=g)
+    return out
+
+
+def _randint32(torch, n, seed, device, lo=-2**31, hi=2**31):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    chunk = 1 << 28
+    for start in range(0, n, chunk):
+        m = min(chunk, n - start)
+        out[start:start + m] = torch.randint(lo, hi, (m,), generator=g, device=device, dtype=torch.int64).to(torch.int32)
+    return out
+
+
+class Timer:
+    def __init__(self, dev, lib, ffi):
+        self.dev, self.lib, self.ffi = dev, lib, ffi
+
+    def event(self):
+        e = C.c_void_p()
+        self.ffi.check(self.lib.agpu_event_create(C.byref(e)), "event_create")
+        return e
+
+    def record(self, e):
+        self.ffi.check(self.lib.agpu_event_record(self.dev.handle, e), "event_record")
+
+    def ms(self, a, b):
+        out = C.c_float(0)
+        self.ffi.check(self.lib.agpu_event_elapsed_ms(a, b, C.byref(out)), "elapsed")
+        return out.value
+
+
+def run(args, rank, world, local_rank, helpers):
+    """returns the JSON dict for --workload cfg1|cfg3|cfg4|cfg5"""
+    import torch
+
+    import arrow_gpu_b200 as ag
+    from arrow_gpu_b200 import _ffi, kernels as K, sharded
+
+    torch.cuda.set_device(local_rank)
+    tdev = torch.device("cuda", local_rank)
+    dev = ag.GpuDevice(local_rank)
+    lib = _ffi.lib()
+    T = Timer(dev, lib, _ffi)
+    keep = []
+    name = args.workload
+    total_rows = args.rows if args.rows_given else ROWS[name]
+    if name in ("cfg4", "cfg5"):
+        b, e = sharded.row_range(total_rows, rank, world)   # strong scaling: the named column is split
+        n = e - b
+        scaling = "strong"
+    else:
+        n = total_rows
+        scaling = "weak"
+    seed = 1000 * rank
+
+    ops = []  # (label, bytes_per_row (per input row unless noted), rows_counted, fn)
+
+    def nullable(arr, p, s):
+        bits = _bitmap(torch, n, p, s, tdev)
+        keep.append(bits)
+        arr.null_buffer = ag.NullBitBufferGpu(ag.ArrowGpuBuffer(dev, bits.data_ptr(), bits.numel(), owned=False), n, dev)
+        return arr
+
+    if name == "cfg1":
+        a = nullable(_wrap(ag, ag.Float32ArrayGPU, _uniform(torch, n, -1000, 1000, 1 + seed, tdev), n, dev, keep), 0.9, 2 + seed)
+        b_ = nullable(_wrap(ag, ag.Float32ArrayGPU, _uniform(torch, n, -1000, 1000, 11 + seed, tdev), n, dev, keep), 0.9, 3 + seed)
+        ops = [("f32.add+validity", 12.375, n, lambda: a.add(b_)), ("f32.gt+validity", 8.5, n, lambda: a.gt(b_))]
+    elif name == "cfg3":
+        cols = [nullable(_wrap(ag, ag.Float32ArrayGPU, _uniform(torch, n, -10, 10, 20 + k + seed, tdev), n, dev, keep), 0.95, 24 + k + seed)
+                for k in range(4)]
+
+        def chain():
+            p = ag.ArrowComputePipeline(dev, "chain")
+            r = K.gt_op_dyn(K.add_op_dyn(K.mul_op_dyn(cols[0], cols[1], p), cols[2], p), cols[3], p)
+            p.finish()
+            return r
+        ops = [("fused (a*b+c)>d + 4 bitmaps", 16.75, n, lambda: K.fused_mul_add_gt(*cols)),
+               ("unfused chain mul,add,gt (reference style, 3 kernels)", 33.25, n, chain)]
+    elif name == "cfg4":
+        rng = {"sqrt": (0, 1e6), "exp": (-20, 20), "sin": (-100, 100), "cos": (-100, 100)}
+        col = {}
+        for k, (op, (lo, hi)) in enumerate(rng.items()):
+            if (lo, hi) not in col:
+                col[(lo, hi)] = _wrap(ag, ag.Float32ArrayGPU, _uniform(torch, n, lo, hi, 30 + k + seed, tdev), n, dev, keep)
+            arr = col[(lo, hi)]
+            ops.append((f"f32.{op}", 8.0, n, (lambda arr=arr, op=op: getattr(arr, op)())))
+    elif name == "cfg5":
+        a = _wrap(ag, ag.Int32ArrayGPU, _randint32(torch, n, 40 + seed, tdev), n, dev, keep)
+        b_ = _wrap(ag, ag.Int32ArrayGPU, _randint32(torch, n, 140 + seed, tdev), n, dev, keep)
+
+        def mask(p, s):
+            bits = _bitmap(torch, n, p, s, tdev)
+            keep.append(bits)
+            return ag.BooleanArrayGPU(ag.ArrowGpuBuffer(dev, bits.data_ptr(), bits.numel(), owned=False), dev, n, None)
+        m50 = mask(0.5, 41 + seed)
+        ops.append(("i32.merge", 12.125, n, lambda: a.merge(b_, m50)))
+        for s, sd in ((0.1, 42), (0.5, 43), (0.9, 44)):
+            mk = mask(s, sd + seed)
+
+            def filt(mk=mk):
+                out, _off, _tot = sharded.sharded_filter(a, mk)   # count exchange over NCCL when world > 1
+                return out
+            ops.append((f"i32.filter s={s}", 4.125 + 4 * s, n, filt))
+        seq = torch.arange(n, dtype=torch.int64, device=tdev).to(torch.int32)
+        idx_seq = _wrap(ag, ag.UInt32ArrayGPU, seq, n, dev, keep)
+        idx_rnd = _wrap(ag, ag.UInt32ArrayGPU, _randint32(torch, n, 45 + seed, tdev, 0, n), n, dev, keep)
+        ops.append(("i32.take sorted stride-1", 12.0, n, lambda: a.take(idx_seq)))
+        ops.append(("i32.take uniform random", 12.0, n, lambda: a.take(idx_rnd)))
+    else:
+        raise SystemExit(f"unknown workload {name}")
+
+    torch.cuda.synchronize()
+    flush = None
+    if name == "cfg1":   # columns fit in L2: flush it between timed iterations
+        flush = dev.create_empty_buffer(512 << 20)
+
+    def one(fn):
+        out = fn()
+        del out
+
+    for _ in range(args.warmup):
+        for _l, _b, _r, fn in ops:
+            one(fn)
+    dev.sync()
+    sharded.barrier()
+    clocks_proc = helpers["clocks_start"](local_rank)
+    launches0 = dev.launch_count()
+    per = {label: [] for label, *_ in ops}
+    for _ in range(args.steps):
+        for label, _b, _r, fn in ops:
+            if flush is not None:
+                _ffi.check(lib.agpu_memset(dev.handle, flush.ptr, 0, flush.size), "flush")
+            e0, e1 = T.event(), T.event()
+            T.record(e0)
+            one(fn)
+            T.record(e1)
+            dev.sync()
+            per[label].append(T.ms(e0, e1))
+    launches = dev.launch_count() - launches0
+    clocks = helpers["clocks_stop"](clocks_proc)
+    sharded.barrier()
+
+    peak, peak_src = helpers["peak"]()
+    per_op, total_ms, total_rows_done = {}, 0.0, 0
+    for label, bpr, rows_counted, _fn in ops:
+        ms = sharded.max_over_ranks(statistics.mean(per[label]))
+        gbs = bpr * rows_counted / (ms * 1e-3) / 1e9          # per GPU
+        per_op[label] = {"ms": round(ms, 4), "rows_per_s": rows_counted * world / (ms * 1e-3), "GBps_per_gpu": round(gbs, 1),
+                         "B_per_row": bpr, "frac_measured_peak": round(gbs / peak, 4), "frac_8TBps": round(gbs / 8000, 4)}
+        total_ms += ms
+        total_rows_done += rows_counted * world
+    worst = max(per_op, key=lambda k: per_op[k]["ms"])
+    res = {
+        "metric": f"rows/s (row-operations per second over the ops of {name}; achieved HBM GB/s per op in per_op)",
+        "value": total_rows_done / (total_ms * 1e-3), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(total_ms, 4), "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f32" if name != "cfg5" else "i32", "data": "synthetic (generated on device, seeded)",
+        "config": {"workload": f"BASELINE.json {name}", "rows_total": total_rows, "rows_per_gpu": n,
+                   "l2": "L2 flushed between iterations" if flush is not None else "inputs larger than L2"},
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": None,
+        "roofline": {"bound": "hbm", "kernel": worst, "achieved": per_op[worst]["GBps_per_gpu"], "peak": peak, "unit": "GB/s",
+                     "frac": per_op[worst]["frac_measured_peak"], "traffic": helpers["traffic"](worst), "peak_source": peak_src},
+        "per_op": per_op, "cpu_baseline": None,
+    }
+    return res

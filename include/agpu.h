@@ -228,10 +228,10 @@ int agpu_put(agpu_device* dev, int dtype, const void* src, const uint32_t* src_i
  * Keeps rows whose mask bit is 1 and (if vmask) whose mask is valid, order preserving.
  * Two calls so a sharded caller can learn the count (and exchange it between GPUs) before it
  * allocates the output:
- *   agpu_filter_count  : per-tile selected-row counts into `scratch`
- *                        (agpu_filter_scratch_bytes(n) bytes, 16-byte aligned) and the total
- *                        into *total_dev (a device uint64)
- *   agpu_filter_scatter: scans the tile counts in `scratch`, then compacts the values into
+ *   agpu_filter_count  : per-tile selected-row counts and scanned per-group output offsets
+ *                        into `scratch` (agpu_filter_scratch_bytes(n) bytes, 16-byte aligned)
+ *                        and the total into *total_dev (a device uint64)
+ *   agpu_filter_scatter: uses the counts/offsets in `scratch` to compact the values into
  *                        out[0 .. total) and, when vsrc and vout are given, the validity bits
  *                        into vout (which must hold ceil(n/32) words; it is zeroed first). */
 size_t agpu_filter_scratch_bytes(size_t n);
