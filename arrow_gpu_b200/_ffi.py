@@ -47,6 +47,7 @@ SIGNATURES = {
     "agpu_event_destroy": (_i, [_p]),
     "agpu_event_record": (_i, [_p, _p]),
     "agpu_event_elapsed_ms": (_i, [_p, _p, C.POINTER(C.c_float)]),
+    "agpu_stream_wait_event": (_i, [_p, _p]),
     "agpu_validity_and": (_i, [_p, _u32p, _u32p, _u32p, _sz]),
     "agpu_binary": (_i, [_p, _i, _i, _p, _p, _p, _sz, _u32p, _u32p, _u32p]),
     "agpu_scalar": (_i, [_p, _i, _i, _p, _p, _p, _sz, _u32p, _u32p]),

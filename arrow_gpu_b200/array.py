@@ -142,8 +142,39 @@ class GpuDevice:
     def sync(self) -> None:
         check(lib().agpu_sync(self.handle), "agpu_sync")
 
+    # --- events (CmpQuery of the reference, gpu_utils/compute_query.rs) and cross-stream order
+    def record_event(self, event: Optional["GpuEvent"] = None) -> "GpuEvent":
+        event = event or GpuEvent()
+        check(lib().agpu_event_record(self.handle, event.handle), "agpu_event_record")
+        return event
+
+    def wait_event(self, event: "GpuEvent") -> None:
+        """later work of this device handle waits on the GPU for `event` (recorded by another
+        handle of the same GPU, e.g. an upload stream)"""
+        check(lib().agpu_stream_wait_event(self.handle, event.handle), "agpu_stream_wait_event")
+
     def launch_count(self) -> int:
         return int(lib().agpu_launch_count(self.handle))
+
+
+class GpuEvent:
+    def __init__(self):
+        h = C.c_void_p()
+        check(lib().agpu_event_create(C.byref(h)), "agpu_event_create")
+        self.handle = h
+
+    def elapsed_ms(self, later: "GpuEvent") -> float:
+        ms = C.c_float(0)
+        check(lib().agpu_event_elapsed_ms(self.handle, later.handle, C.byref(ms)), "agpu_event_elapsed_ms")
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().agpu_event_destroy(self.handle)
+        except Exception:
+            pass
+        self.handle = None
 
 
 class ArrowGpuBuffer:

@@ -178,6 +178,13 @@ extern "C" int agpu_event_record(agpu_device* dev, agpu_event* ev) {
   return 0;
 }
 
+extern "C" int agpu_stream_wait_event(agpu_device* dev, agpu_event* ev) {
+  if (!dev) return AGPU_ENODEVICE;
+  AGPU_REQUIRE(ev);
+  AGPU_CUDA(cudaStreamWaitEvent(dev->stream, ev->ev, 0));
+  return 0;
+}
+
 extern "C" int agpu_event_elapsed_ms(agpu_event* start, agpu_event* stop, float* ms) {
   AGPU_REQUIRE(start && stop && ms);
   AGPU_CUDA(cudaEventSynchronize(stop->ev));

@@ -259,16 +259,39 @@ def run_ours(args, rank, world, local_rank):
     value = row_ops * world / (total_ms * 1e-3)
 
     # ---- end to end through the public API from pinned host buffers ----
+    # A second device handle (= a second stream on the same GPU) uploads the input columns while
+    # the compute handle works; each op waits on the GPU for the upload events of its inputs.
+    # Outputs are read back on the compute stream into a pinned landing buffer.  PCIe is full
+    # duplex, so H2D hides behind the (larger) D2H traffic.
+    up = ag.GpuDevice(local_rank)
+    order = []
+    for spec in ops:
+        for c in inputs_of(spec):
+            if c not in order:
+                order.append(c)
+
     def e2e_step():
-        live = {name: upload(name, False) for name in pinned}
+        live, ready = {}, {}
+        for name in order:
+            c = col_cls.get(name) or cls[name.split(".")[0]]
+            arr = c.from_numpy(pinned[name], None, up, wait=False)
+            ready[name] = up.record_event()
+            arr.gpu_device = dev          # ops on this column run on the compute handle
+            live[name] = arr
         h2d = sum(a.nbytes for a in pinned.values())
         d2h = 0
+        waited = set()
         for spec in ops:
+            for c in inputs_of(spec):
+                if c not in waited:
+                    dev.wait_event(ready[c])
+                    waited.add(c)
             out = run(spec, live, scalars)
             view = out_stage[: out.len * out.NP.itemsize].view(out.NP)
             out.raw_values(out=view, wait=False)
             d2h += view.nbytes
         dev.sync()
+        up.sync()
         return h2d, d2h
 
     e2e = None
@@ -393,6 +416,8 @@ def main():
         return
 
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO
+        os.environ["NCCL_DEBUG"] = os.environ.get("AGPU_NCCL_DEBUG", "WARN")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

@@ -183,6 +183,8 @@ def run(args, rank, world, local_rank, helpers):
         for label, _b, _r, fn in ops:
             if flush is not None:
                 _ffi.check(lib.agpu_memset(dev.handle, flush.ptr, 0, flush.size), "flush")
+            if world > 1:
+                sharded.barrier()   # ranks start each op together: rank skew is not the op's cost
             e0, e1 = T.event(), T.event()
             T.record(e0)
             one(fn)

@@ -141,6 +141,9 @@ int agpu_event_create(agpu_event** out);
 int agpu_event_destroy(agpu_event* ev);
 int agpu_event_record(agpu_device* dev, agpu_event* ev);
 int agpu_event_elapsed_ms(agpu_event* start, agpu_event* stop, float* ms); /* waits for stop */
+/* make all later work of `dev` wait (on the GPU, not the host) for an event recorded on another
+ * handle's stream: lets an upload stream run ahead of the compute stream */
+int agpu_stream_wait_event(agpu_device* dev, agpu_event* ev);
 
 /* ---- validity bitmaps: NullBitBufferGpu (crates/array/src/array/null_bit_buffer.rs) ---- */
 
