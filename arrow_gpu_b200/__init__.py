@@ -10,3 +10,4 @@ from .array import *  # noqa: F401,F403
 from .array import GPU_DEVICE, ARRAY_BY_NAME, ARRAY_TYPES  # noqa: F401
 from .kernels import *  # noqa: F401,F403
 from . import kernels  # noqa: F401
+from .interop import from_arrow, to_arrow  # noqa: F401,E402

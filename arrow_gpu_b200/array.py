@@ -153,6 +153,11 @@ class GpuDevice:
         handle of the same GPU, e.g. an upload stream)"""
         check(lib().agpu_stream_wait_event(self.handle, event.handle), "agpu_stream_wait_event")
 
+    @property
+    def stream_ptr(self) -> int:
+        """the cudaStream_t of this handle (e.g. for torch.cuda.ExternalStream)"""
+        return int(lib().agpu_device_stream(self.handle) or 0)
+
     def launch_count(self) -> int:
         return int(lib().agpu_launch_count(self.handle))
 
@@ -205,14 +210,22 @@ class ArrowComputePipeline:
     queues, so every `*_op` enqueues its kernel immediately on the device's stream and
     `finish()` only marks the end of the scope (it never waits, like the reference)."""
 
-    def __init__(self, device: GpuDevice, label: Optional[str] = None):
+    def __init__(self, device: GpuDevice, label: Optional[str] = None, profile: bool = False):
         self.device = device
         self.label = label
         self.finished = False
+        # the reference's `profile` cargo feature wraps every compute pass in timestamp queries
+        # (gpu_utils/compute_query.rs:3-90); here: a CUDA event pair per recorded op
+        self.profile = profile
+        self.queries: list = []
 
     @classmethod
     def new(cls, device: GpuDevice, label: Optional[str] = None) -> "ArrowComputePipeline":
         return cls(device, label)
+
+    def wait_for_results(self) -> list:
+        """compute_query.rs:54-75: [(op name, milliseconds)] of every op recorded with profile=True"""
+        return [(name, start.elapsed_ms(stop)) for name, start, stop in self.queries]
 
     def clone_buffer(self, buffer: ArrowGpuBuffer) -> ArrowGpuBuffer:
         return self.device.clone_buffer(buffer)
@@ -311,10 +324,10 @@ class NullBitBufferGpu:
 
     def raw_values(self) -> np.ndarray:
         """bytes of the bitmap, ceil(len/8) of them (null_bit_buffer.rs:124-128)"""
-        return self.gpu_device.retrive_data(self.bit_buffer)[: _round_up(self.len, 8) // 8]
+        return self.gpu_device.retrive_data(self.bit_buffer, bitmap_words(self.len) * 4)[: _round_up(self.len, 8) // 8]
 
     def flags(self) -> np.ndarray:
-        return unpack_bits(self.gpu_device.retrive_data(self.bit_buffer), self.len)
+        return unpack_bits(self.gpu_device.retrive_data(self.bit_buffer, bitmap_words(self.len) * 4), self.len)
 
     @staticmethod
     def clone_null_bit_buffer(data: Optional["NullBitBufferGpu"]) -> Optional["NullBitBufferGpu"]:

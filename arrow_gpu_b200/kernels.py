@@ -553,29 +553,51 @@ def _put_op(self, src_indexes, dst, dst_indexes, pipeline):
                          dst_indexes.data.ptr, src_indexes.len), "put")
 
 
-def _filter_op(self, mask, pipeline):
-    """New surface (BASELINE.json config 5; the reference has no filter): keep rows whose mask
-    bit is set and valid, order preserving.  Needs the selected count on the host to size the
-    output — the one extra synchronisation of this op."""
+class FilterPlan:
+    """state between the two halves of a filter: per-tile counts / scanned offsets (scratch) and
+    the device-side total.  A sharded caller exchanges totals between the halves."""
+
+    def __init__(self, array, mask, scratch, total):
+        self.array, self.mask, self.scratch, self.total = array, mask, scratch, total
+
+
+def _filter_count_op(self, mask, pipeline, total_ptr=None) -> FilterPlan:
+    """first half of filter: count the selected rows (one pass over the mask bits).  `total_ptr`
+    may point at caller-owned device memory (8 bytes) that receives the count."""
     if not isinstance(mask, BooleanArrayGPU) or isinstance(self, BooleanArrayGPU):
         raise Panic(f"Filter Operation not supported for {self.get_dtype()}")
     _check_same_len(self, mask, "filter")
     dev = self.gpu_device
     l = lib()
     scratch = dev.create_empty_buffer(l.agpu_filter_scratch_bytes(self.len))
-    total = dev.create_empty_buffer(8)
-    check(l.agpu_filter_count(dev.handle, mask.data.ptr, _vptr(mask.null_buffer), self.len, scratch.ptr, total.ptr),
-          "filter_count")
-    count = int(dev.retrive_data(total, 8).view(np.uint64)[0])
+    total = None if total_ptr is not None else dev.create_empty_buffer(8)
+    check(l.agpu_filter_count(dev.handle, mask.data.ptr, _vptr(mask.null_buffer), self.len, scratch.ptr,
+                              total_ptr if total_ptr is not None else total.ptr), "filter_count")
+    return FilterPlan(self, mask, scratch, total)
+
+
+def _filter_scatter_op(self, plan: FilterPlan, count: int, pipeline):
+    """second half of filter: compact values (and validity) into a `count`-row array"""
+    dev = self.gpu_device
+    mask = plan.mask
     out = type(self).empty(count, dev)
     vout = None
     if self.null_buffer is not None:
         vout = dev.create_empty_buffer(bitmap_words(self.len) * 4 + 4)
         out.null_buffer = NullBitBufferGpu(vout, count, dev)
-    check(l.agpu_filter_scatter(dev.handle, self.DTYPE, self.data.ptr, _vptr(self.null_buffer), mask.data.ptr,
-                                _vptr(mask.null_buffer), self.len, scratch.ptr, out.data.ptr,
-                                vout.ptr if vout else None), "filter_scatter")
+    check(lib().agpu_filter_scatter(dev.handle, self.DTYPE, self.data.ptr, _vptr(self.null_buffer), mask.data.ptr,
+                                    _vptr(mask.null_buffer), self.len, plan.scratch.ptr, out.data.ptr,
+                                    vout.ptr if vout else None), "filter_scatter")
     return out
+
+
+def _filter_op(self, mask, pipeline):
+    """New surface (BASELINE.json config 5; the reference has no filter): keep rows whose mask
+    bit is set and valid, order preserving.  Needs the selected count on the host to size the
+    output — the one extra synchronisation of this op."""
+    plan = _filter_count_op(self, mask, pipeline)
+    count = int(self.gpu_device.retrive_data(plan.total, 8).view(np.uint64)[0])
+    return _filter_scatter_op(self, plan, count, pipeline)
 
 
 for _cls in (PrimitiveArrayGpu, BooleanArrayGPU):
@@ -587,6 +609,8 @@ for _cls in (PrimitiveArrayGpu, BooleanArrayGPU):
     _cls.put = _eager(_put_op)
 PrimitiveArrayGpu.filter_op = _filter_op
 PrimitiveArrayGpu.filter = _eager(_filter_op)
+PrimitiveArrayGpu.filter_count_op = _filter_count_op
+PrimitiveArrayGpu.filter_scatter_op = _filter_scatter_op
 
 
 def merge_op_dyn(operand_1, operand_2, mask, pipeline):
@@ -657,3 +681,27 @@ def fused_mul_add_gt(a, b, c, d) -> BooleanArrayGPU:
     out = fused_mul_add_gt_op(a, b, c, d, pipeline)
     pipeline.finish()
     return out
+
+
+# ==========================================================================================
+# profiling hook (the reference's `profile` feature, gpu_utils/compute_query.rs): every `*_op`
+# recorded on a pipeline created with profile=True is bracketed by a CUDA event pair
+# ==========================================================================================
+def _profiled(name, fn):
+    def wrapper(self, *args, **kwargs):
+        pipeline = next((a for a in reversed(args) if isinstance(a, ArrowComputePipeline)), None)
+        if pipeline is not None and pipeline.profile:
+            start = pipeline.device.record_event()
+            out = fn(self, *args, **kwargs)
+            pipeline.queries.append((name, start, pipeline.device.record_event()))
+            return out
+        return fn(self, *args, **kwargs)
+    wrapper.__name__ = getattr(fn, "__name__", name)
+    wrapper.__doc__ = fn.__doc__
+    return wrapper
+
+
+for _cls in (PrimitiveArrayGpu, BooleanArrayGPU):
+    for _name, _fn in list(vars(_cls).items()):
+        if _name.endswith("_op") and callable(_fn) and not isinstance(_fn, (classmethod, staticmethod)):
+            setattr(_cls, _name, _profiled(_name, _fn))

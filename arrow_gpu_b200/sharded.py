@@ -85,10 +85,33 @@ def barrier() -> None:
 
 
 def sharded_filter(array, mask):
-    """Filter this rank's shard and report where its output sits in the global result:
-    returns (local filtered array, global offset of its first row, global row count)."""
-    out = array.filter(mask)
-    offsets, total = exchange_counts(out.len)
+    """Filter this rank's shard and learn where its output sits in the global result:
+    returns (local filtered array, global offset of its first row, global row count).
+
+    On GPUs (NCCL) the per-shard counts never leave the device before the exchange: the count
+    kernel writes this rank's total into a device word, `all_gather_into_tensor` runs on the SAME
+    stream (torch sees the library's stream as an ExternalStream), and one 8*world-byte readback
+    gives every rank all counts — a single host synchronisation per filter instead of one for the
+    local count plus one per gathered value."""
     dist = _dist()
-    rank = dist.get_rank() if dist is not None else 0
+    if dist is None or dist.get_backend() != "nccl":
+        out = array.filter(mask)
+        offsets, total = exchange_counts(out.len)
+        rank = dist.get_rank() if dist is not None else 0
+        return out, offsets[rank], total
+    import torch
+    from .array import ArrowComputePipeline
+    dev = array.gpu_device
+    tdev = torch.device("cuda", dev.ordinal)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    with torch.cuda.stream(torch.cuda.ExternalStream(dev.stream_ptr, device=tdev)):
+        mine = torch.zeros(1, dtype=torch.int64, device=tdev)
+        pipeline = ArrowComputePipeline(dev, "sharded_filter")
+        plan = array.filter_count_op(mask, pipeline, total_ptr=mine.data_ptr())
+        gathered = torch.empty(world, dtype=torch.int64, device=tdev)
+        dist.all_gather_into_tensor(gathered, mine)
+        counts = gathered.cpu().tolist()          # the one synchronisation
+    offsets, total = exclusive_offsets(counts)
+    out = array.filter_scatter_op(plan, int(counts[rank]), pipeline)
+    pipeline.finish()
     return out, offsets[rank], total

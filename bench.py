@@ -401,6 +401,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version
+    # banner there) are sent to stderr, the result goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
     args.rows_given = args.rows is not None
     if args.rows is None:
         args.rows = ROWS_CFG2
@@ -412,12 +421,10 @@ def main():
     if args.impl == "reference":
         res = run_reference(args, rank)
         if res is not None:
-            print(json.dumps(res))
+            emit(res)
         return
 
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("AGPU_NCCL_DEBUG", "WARN")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -429,7 +436,7 @@ def main():
                                       {"clocks_start": sample_clocks_start, "clocks_stop": sample_clocks_stop,
                                        "peak": measured_peak, "traffic": known_traffic})
             if rank == 0:
-                print(json.dumps(res))
+                emit(res)
             return
         res = run_ours(args, rank, world, local_rank)
         if rank == 0:
@@ -437,7 +444,7 @@ def main():
                 res["cpu_baseline"] = time_cpu(args.cpu_rows, 3, 1)
             else:
                 res["cpu_baseline"] = None
-            print(json.dumps(res))
+            emit(res)
     finally:
         if world > 1:
             import torch.distributed as dist

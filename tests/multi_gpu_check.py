@@ -1,0 +1,66 @@
+"""Run under torchrun (one rank per GPU, NCCL):  row-range shards of one global column are
+processed independently; the filter's per-shard counts are exchanged on the device.  Every rank
+checks its shard of the result against numpy applied to the GLOBAL column.
+
+    python -m torch.distributed.run --nproc-per-node N tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import arrow_gpu_b200 as ag
+    from arrow_gpu_b200 import sharded
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = ag.GpuDevice(local)
+    n = 3_000_017                     # not a multiple of the shard alignment
+    rng = np.random.default_rng(123)  # same global column on every rank
+    vals = rng.integers(-2**31, 2**31, n).astype(np.int32)
+    valid = rng.random(n) < 0.9
+    keep = rng.random(n) < 0.37
+    kvalid = rng.random(n) < 0.95
+    other = rng.integers(-2**31, 2**31, n).astype(np.int32)
+
+    b, e = sharded.row_range(n, rank, world)
+    a = ag.Int32ArrayGPU.from_numpy(vals[b:e], valid[b:e], dev)
+    o = ag.Int32ArrayGPU.from_numpy(other[b:e], None, dev)
+    m = ag.BooleanArrayGPU.from_numpy(keep[b:e], kvalid[b:e], dev)
+
+    # element-wise + compare + merge: no communication, shard == slice of the global result
+    assert np.array_equal(a.add(o).raw_values(), (vals[b:e].astype(np.int64) + other[b:e]).astype(np.int32))
+    assert np.array_equal(a.gt(o).raw_values(), vals[b:e] > other[b:e])
+    assert np.array_equal(a.merge(o, m).raw_values(), np.where(keep[b:e], vals[b:e], other[b:e]))
+
+    # filter: local compaction + count exchange -> global placement
+    out, offset, total = sharded.sharded_filter(a, m)
+    sel = keep & kvalid
+    assert total == int(sel.sum()), (total, int(sel.sum()))
+    assert offset == int(sel[:b].sum()), (rank, offset)
+    want = vals[sel]
+    got = out.raw_values()
+    assert np.array_equal(got, want[offset:offset + len(got)])
+    assert np.array_equal(out.null_buffer.flags(), valid[sel][offset:offset + len(got)])
+
+    # the global result reassembled from the shards (all_gather of the ragged pieces via padding)
+    t = torch.zeros(n, dtype=torch.int32, device=f"cuda:{local}")
+    t[offset:offset + len(got)] = torch.from_numpy(got).to(t.device)
+    dist.all_reduce(t)
+    assert np.array_equal(t[:total].cpu().numpy(), want)
+    dist.barrier()
+    if rank == 0:
+        print(f"multi-GPU check ok: world={world}, {total} of {n} rows kept")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -276,3 +276,35 @@ def test_unsupported_pairs_panic(device):
             fn(*args)
     with pytest.raises(ag.Panic):
         K.cast_dyn(i, ag.ArrowType.Float32Type)  # not in the reference's cast matrix
+
+
+def test_pipeline_profile_feature(device):
+    """the reference's `profile` feature (gpu_utils/compute_query.rs): per-op timestamps"""
+    arr = ag.Float32ArrayGPU.from_slice(np.arange(1 << 20, dtype=np.float32), device)
+    sc = ag.Float32ArrayGPU.from_slice([2.0], device)
+    pipeline = ag.ArrowComputePipeline(device, "profiled", profile=True)
+    r = K.mul_scalar_op_dyn(K.add_scalar_op_dyn(arr, sc, pipeline), sc, pipeline)
+    K.gt_op_dyn(r, arr, pipeline)
+    pipeline.finish()
+    res = pipeline.wait_for_results()
+    assert [n for n, _ in res] == ["add_scalar_op", "mul_scalar_op", "gt_op"]
+    assert all(0.0 < ms < 50.0 for _, ms in res)
+
+
+def test_arrow_interop_roundtrip(device):
+    pa = pytest.importorskip("pyarrow")
+    import pyarrow.compute as pc
+    cases = [pa.array([1, None, -3, 4, None], pa.int8()), pa.array([1.5, 2.5, None], pa.float32()),
+             pa.array([True, None, False, True] * 11, pa.bool_()), pa.array(list(range(100)), pa.uint16()),
+             pa.array([None, 7], pa.date32()), pa.array([], pa.int32()), pa.array(list(range(50)), pa.int32())[3:40]]
+    for a in cases:
+        g = ag.from_arrow(a, device)
+        assert g.len == len(a)
+        assert ag.to_arrow(g).equals(a if a.offset == 0 else pa.concat_arrays([a])), a.type
+    # same results as pyarrow.compute where the two agree (SURVEY.md §8c cross-check list)
+    x = pa.array([100, 127, -128, None, 5], pa.int8())
+    y = pa.array([100, 1, -1, 3, None], pa.int8())
+    gx, gy = ag.from_arrow(x, device), ag.from_arrow(y, device)
+    assert ag.to_arrow(gx.add(gy)).equals(pc.add(x, y))            # wrap-around
+    assert ag.to_arrow(gx.gt(gy)).equals(pc.greater(x, y))
+    assert ag.to_arrow(gx.max(gy)).to_pylist() == pc.max_element_wise(x, y, skip_nulls=False).to_pylist()

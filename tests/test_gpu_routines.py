@@ -146,3 +146,20 @@ def test_filter_large_properties(device):
     out = a.filter(m).raw_values()
     assert len(out) == int(flags.sum())
     assert np.array_equal(out, vals[flags])
+
+
+def test_sharded_filter_nccl(device):
+    """row-range shards + device-side NCCL count exchange, one rank per visible GPU (max 2; a
+    single GPU still exercises the NCCL path with world_size 1)"""
+    import os
+    import subprocess
+    import sys
+    import arrow_gpu_b200._ffi as ffi
+    world = min(2, ffi.device_count())
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300),
+           os.path.join(root, "tests", "multi_gpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "multi-GPU check ok" in res.stdout
