@@ -110,14 +110,31 @@ int run_sum(agpu_device* dev, const T* a, size_t n, T* out_dev) {
 // mode 0 (any): flag when a word has a set bit; mode 1 (all): flag when a word has a clear bit
 // among the first n_bits.  `all` is finished by flipping the flag.
 __global__ void __launch_bounds__(kBlock) bits_find_kernel(const uint32_t* __restrict__ bits, const size_t nwords,
-                                                           const size_t n_bits, const int mode,
+                                                           const size_t n_bits, const int mode, const int vec,
                                                            uint32_t* __restrict__ flag) {
   const uint32_t tail_mask = (n_bits & 31) ? ((1u << (n_bits & 31)) - 1u) : 0xFFFFFFFFu;
+  const uint32_t flip = mode == 0 ? 0u : 0xFFFFFFFFu;  // all: look for a clear bit
   uint32_t found = 0;
-  for (size_t w = (size_t)blockIdx.x * kBlock + threadIdx.x; w < nwords; w += (size_t)gridDim.x * kBlock) {
-    uint32_t x = __ldcs(bits + w);
-    const uint32_t m = (w == nwords - 1) ? tail_mask : 0xFFFFFFFFu;
-    x = mode == 0 ? (x & m) : (~x & m);
+  // body: whole 16-byte chunks except the one holding the last word, 4 chunks in flight per thread
+  const size_t nvec = vec ? (nwords - 1) / 4 : 0;
+  const uint4* __restrict__ v = reinterpret_cast<const uint4*>(bits);
+  const size_t stride = (size_t)gridDim.x * kBlock;
+  size_t q = (size_t)blockIdx.x * kBlock + threadIdx.x;
+  for (; q + 3 * stride < nvec; q += 4 * stride) {
+    uint4 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = __ldcs(v + q + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) found |= (x[k].x ^ flip) | (x[k].y ^ flip) | (x[k].z ^ flip) | (x[k].w ^ flip);
+  }
+  for (; q < nvec; q += stride) {
+    const uint4 x = __ldcs(v + q);
+    found |= (x.x ^ flip) | (x.y ^ flip) | (x.z ^ flip) | (x.w ^ flip);
+  }
+  // leftover words (at most 4 with vector access, everything otherwise), the last one masked
+  for (size_t w = nvec * 4 + (size_t)blockIdx.x * kBlock + threadIdx.x; w < nwords; w += stride) {
+    uint32_t x = bits[w] ^ flip;
+    if (w == nwords - 1) x &= tail_mask;
     found |= x;
   }
   found = __reduce_or_sync(0xFFFFFFFFu, found);
@@ -156,10 +173,12 @@ static int find_bits(agpu_device* dev, const uint32_t* bits, size_t n_bits, int 
   AGPU_CUDA(cudaMemsetAsync(result_dev, 0, 4, dev->stream));
   const size_t nwords = (n_bits + 31) / 32;
   if (nwords) {
-    size_t grid = ceil_div(nwords, (size_t)kBlock);
-    const size_t cap = (size_t)dev->sm_count * 16;
+    size_t grid = ceil_div(nwords, (size_t)kBlock * 16);
+    const size_t cap = (size_t)dev->sm_count * 32;
     if (grid > cap) grid = cap;
-    AGPU_LAUNCH(dev, bits_find_kernel, (unsigned)grid, kBlock, 0, bits, nwords, n_bits, mode, result_dev);
+    if (grid == 0) grid = 1;
+    AGPU_LAUNCH(dev, bits_find_kernel, (unsigned)grid, kBlock, 0, bits, nwords, n_bits, mode, aligned16(bits) ? 1 : 0,
+                result_dev);
   }
   if (mode == 1) AGPU_LAUNCH(dev, flip_flag_kernel, 1, 1, 0, result_dev);
   return agpu_finish_launch();

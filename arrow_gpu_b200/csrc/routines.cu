@@ -1,6 +1,8 @@
 // routines.cu — merge (mask select), take (gather), put (scatter) and filter (compaction):
 // crates/routines.  merge/take/put follow the reference shaders; filter is new surface
 //  built from warp-level prefix sums with shared-memory staging.
+#include <stdlib.h>
+
 #include "bits.cuh"
 #include "elementwise.cuh"
 
@@ -332,8 +334,8 @@ __global__ void __launch_bounds__(1024) filter_scan_kernel(uint64_t* __restrict_
   if (threadIdx.x == 0) *total = carry_s;
 }
 
-template <typename U, bool HAS_V>
-__global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restrict__ src,
+template <typename U, bool HAS_V, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restrict__ src,
                                                                 const uint32_t* __restrict__ vsrc,
                                                                 const uint32_t* __restrict__ mask,
                                                                 const uint32_t* __restrict__ vmask, const size_t n,
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restr
                                                                 const uint64_t* __restrict__ group_offsets,
                                                                 U* __restrict__ out, uint32_t* vout) {
   constexpr int G = 16 / sizeof(U);                   // rows per 16-byte granule
-  constexpr int GPT = kFilterTileRows / G / kBlock;    // granules per thread
+  constexpr int GPT = kFilterTileRows / G / BLOCK;    // granules per thread
   __shared__ __align__(16) U stage[kFilterTileRows + G];
   __shared__ uint32_t sel[kFilterTileWords];
   __shared__ uint32_t pre[kFilterTileWords];
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restr
   Vec<U, G> v[GPT];
   if (full) {
 #pragma unroll
-    for (int j = 0; j < GPT; ++j) v[j] = ld_vec<U, G>(src + row0, (size_t)j * kBlock + threadIdx.x);
+    for (int j = 0; j < GPT; ++j) v[j] = ld_vec<U, G>(src + row0, (size_t)j * BLOCK + threadIdx.x);
   }
   uint32_t before = 0;
   uint64_t goff = 0;
@@ -371,9 +373,9 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restr
     if (gstart + 32 + lane < tile) before += counts[gstart + 32 + lane];
     if (lane == 0) goff = group_offsets[tile / kFilterGroupTiles];
   }
-  if (threadIdx.x < kFilterTileWords) {
-    sel[threadIdx.x] = sel_word(mask, vmask, w0 + threadIdx.x, nwords, n);
-    if (HAS_V) vstage[threadIdx.x] = 0u;
+  for (int w = threadIdx.x; w < kFilterTileWords; w += BLOCK) {
+    sel[w] = sel_word(mask, vmask, w0 + w, nwords, n);
+    if (HAS_V) vstage[w] = 0u;
   }
   if (HAS_V && threadIdx.x == 0) vstage[kFilterTileWords] = 0u;
   if (warp == 1) {
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restr
 
 #pragma unroll
   for (int j = 0; j < GPT; ++j) {
-    const int r = (j * kBlock + threadIdx.x) * G;  // first row of the granule within the tile
+    const int r = (j * BLOCK + threadIdx.x) * G;  // first row of the granule within the tile
     const uint32_t sw = sel[r >> 5];
     const uint32_t bits = (sw >> (r & 31)) & ((1u << G) - 1u);
     if (bits == 0) continue;
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restr
     U* gbase = out + (off - lead);
     const uint32_t end = lead + count;
     const uint32_t nvec = (end + G - 1) / G;
-    for (uint32_t q = threadIdx.x; q < nvec; q += kBlock) {
+    for (uint32_t q = threadIdx.x; q < nvec; q += BLOCK) {
       const uint32_t e0 = q * G;
       if (e0 >= lead && e0 + G <= end) {
         Vec<U, G> t = *reinterpret_cast<const Vec<U, G>*>(stage + e0);
@@ -441,18 +443,245 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_kernel(const U* __restr
       }
     }
   } else {
-    for (uint32_t i = threadIdx.x; i < count; i += kBlock) out[off + i] = stage[i];
+    for (uint32_t i = threadIdx.x; i < count; i += BLOCK) out[off + i] = stage[i];
   }
   if (HAS_V) {
     const uint32_t lw_n = (count + 31) / 32;
     const uint32_t s = (uint32_t)(off & 31);
-    if (threadIdx.x < lw_n) {
-      const uint32_t val = vstage[threadIdx.x];
-      const uint64_t gw = (off >> 5) + threadIdx.x;
+    for (uint32_t w = threadIdx.x; w < lw_n; w += BLOCK) {
+      const uint32_t val = vstage[w];
+      const uint64_t gw = (off >> 5) + w;
       if (val << s) atomicOr(vout + gw, val << s);
       if (s && (val >> (32 - s))) atomicOr(vout + gw + 1, val >> (32 - s));
     }
   }
+}
+
+// --------------------------------------------------------------------------------------------
+// TMA-staged variant of the scatter pass (opt-in with AGPU_FILTER_TMA=1; measured slower, see
+// run_filter).
+// Persistent CTAs walk tiles round-robin.  The 16 KiB of rows of the NEXT tile are fetched by
+// one bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier) while
+// the CTA prefix-sums, compacts and streams out the CURRENT tile, so HBM reads never pause for
+// the per-tile barriers.  Shared memory: 2 raw row buffers + 1 compaction stage.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename U>
+struct FilterTmaSmem {
+  static constexpr int G = 16 / sizeof(U);
+  alignas(128) U raw[2][kFilterTileRows];
+  alignas(16) U stage[kFilterTileRows + G];
+  uint32_t sel[kFilterTileWords];
+  uint32_t pre[kFilterTileWords];
+  uint32_t vstage[kFilterTileWords + 1];
+  alignas(8) uint64_t bar[2];
+  uint64_t off;
+  uint32_t count;
+};
+
+template <typename U, bool HAS_V>
+__global__ void __launch_bounds__(kBlock) filter_scatter_tma_kernel(const U* __restrict__ src,
+                                                                    const uint32_t* __restrict__ vsrc,
+                                                                    const uint32_t* __restrict__ mask,
+                                                                    const uint32_t* __restrict__ vmask, const size_t n,
+                                                                    const uint32_t* __restrict__ counts,
+                                                                    const uint64_t* __restrict__ group_offsets,
+                                                                    U* __restrict__ out, uint32_t* vout) {
+  constexpr int G = 16 / sizeof(U);
+  constexpr int GPT = kFilterTileRows / G / kBlock;
+  constexpr uint32_t kTileBytes = kFilterTileRows * sizeof(U);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FilterTmaSmem<U>& sm = *reinterpret_cast<FilterTmaSmem<U>*>(smem_raw);
+
+  const size_t nwords = (n + 31) / 32;
+  const size_t tiles = (n + kFilterTileRows - 1) / kFilterTileRows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool vec_out = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  size_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < tiles && (tile + 1) * kFilterTileRows <= n) {
+    mbar_expect_tx(&sm.bar[0], kTileBytes);
+    tma_load_1d(sm.raw[0], src + tile * kFilterTileRows, kTileBytes, &sm.bar[0]);
+  }
+  uint32_t parity0 = 0, parity1 = 0;
+  // per-tile metadata (selection word, counts of the earlier tiles of the group, group offset) is
+  // fetched one tile ahead into registers, like the rows, so no global-memory latency is exposed
+  // between the barriers of a tile
+  auto meta_sel = [&](size_t t) -> uint32_t {
+    return (threadIdx.x < kFilterTileWords && t < tiles) ? sel_word(mask, vmask, t * kFilterTileWords + threadIdx.x, nwords, n) : 0u;
+  };
+  auto meta_before = [&](size_t t) -> uint32_t {
+    uint32_t b = 0;
+    if (warp == 1 && t < tiles) {
+      const size_t gstart = t / kFilterGroupTiles * kFilterGroupTiles;
+      if (gstart + lane < t) b += counts[gstart + lane];
+      if (gstart + 32 + lane < t) b += counts[gstart + 32 + lane];
+    }
+    return b;
+  };
+  auto meta_goff = [&](size_t t) -> uint64_t {
+    return (warp == 1 && lane == 0 && t < tiles) ? group_offsets[t / kFilterGroupTiles] : 0ull;
+  };
+  uint32_t cur_sel = meta_sel(tile), cur_before = meta_before(tile);
+  uint64_t cur_goff = meta_goff(tile);
+  for (int it = 0; tile < tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const size_t row0 = tile * kFilterTileRows;
+    const bool full = row0 + kFilterTileRows <= n;
+    // prefetch the rows of this CTA's next tile into the other buffer (its last readers passed
+    // the barrier that ends the previous iteration)
+    const size_t next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < tiles && (next + 1) * kFilterTileRows <= n) {
+      mbar_expect_tx(&sm.bar[buf ^ 1], kTileBytes);
+      tma_load_1d(sm.raw[buf ^ 1], src + next * kFilterTileRows, kTileBytes, &sm.bar[buf ^ 1]);
+    }
+    const uint32_t nxt_sel = meta_sel(next), nxt_before = meta_before(next);
+    const uint64_t nxt_goff = meta_goff(next);
+    if (threadIdx.x < kFilterTileWords) {
+      sm.sel[threadIdx.x] = cur_sel;
+      if (HAS_V) sm.vstage[threadIdx.x] = 0u;
+    }
+    if (HAS_V && threadIdx.x == 0) sm.vstage[kFilterTileWords] = 0u;
+    if (warp == 1) {
+      uint32_t before = cur_before;
+#pragma unroll
+      for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
+      if (lane == 0) sm.off = cur_goff + before;
+    }
+    cur_sel = nxt_sel;
+    cur_before = nxt_before;
+    cur_goff = nxt_goff;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t c[4], s = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { c[k] = __popc(sm.sel[lane * 4 + k]); s += c[k]; }
+      uint32_t incl = s;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += x;
+      }
+      uint32_t e = incl - s;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { sm.pre[lane * 4 + k] = e; e += c[k]; }
+      if (lane == 31) sm.count = incl;
+    }
+    __syncthreads();
+    const uint32_t count = sm.count;
+    const uint64_t off = sm.off;
+    const uint32_t lead = vec_out ? (uint32_t)(off % G) : 0u;
+    if (full) {  // every thread observes the completion of this buffer's bulk copy
+      mbar_wait(&sm.bar[buf], buf ? parity1 : parity0);
+      if (buf) parity1 ^= 1; else parity0 ^= 1;
+    }
+    if (count) {
+      const U* rows = sm.raw[buf];
+#pragma unroll
+      for (int j = 0; j < GPT; ++j) {
+        const int r = (j * kBlock + threadIdx.x) * G;
+        const uint32_t sw = sm.sel[r >> 5];
+        const uint32_t bits = (sw >> (r & 31)) & ((1u << G) - 1u);
+        if (bits == 0) continue;
+        uint32_t pos = lead + sm.pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
+        uint32_t vw = 0;
+        if (HAS_V) vw = vsrc[(row0 + r) >> 5] >> (r & 31);
+        Vec<U, G> v;
+        if (full) v = *reinterpret_cast<const Vec<U, G>*>(rows + r);
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          if ((bits >> k) & 1u) {
+            sm.stage[pos] = full ? v.e[k] : src[row0 + r + k];
+            if (HAS_V && ((vw >> k) & 1u)) atomicOr(&sm.vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
+            ++pos;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (count) {
+      if (vec_out) {
+        U* gbase = out + (off - lead);
+        const uint32_t end = lead + count;
+        const uint32_t nvec = (end + G - 1) / G;
+        for (uint32_t q = threadIdx.x; q < nvec; q += kBlock) {
+          const uint32_t e0 = q * G;
+          if (e0 >= lead && e0 + G <= end) {
+            Vec<U, G> t = *reinterpret_cast<const Vec<U, G>*>(sm.stage + e0);
+            st_vec<U, G>(gbase, q, t);
+          } else {
+            for (uint32_t k = 0; k < (uint32_t)G; ++k)
+              if (e0 + k >= lead && e0 + k < end) gbase[e0 + k] = sm.stage[e0 + k];
+          }
+        }
+      } else {
+        for (uint32_t i = threadIdx.x; i < count; i += kBlock) out[off + i] = sm.stage[i];
+      }
+      if (HAS_V) {
+        const uint32_t lw_n = (count + 31) / 32;
+        const uint32_t s = (uint32_t)(off & 31);
+        if (threadIdx.x < lw_n) {
+          const uint32_t val = sm.vstage[threadIdx.x];
+          const uint64_t gw = (off >> 5) + threadIdx.x;
+          if (val << s) atomicOr(vout + gw, val << s);
+          if (s && (val >> (32 - s))) atomicOr(vout + gw + 1, val >> (32 - s));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename U, bool HAS_V>
+int launch_filter_tma(agpu_device* dev, const U* src, const uint32_t* vsrc, const uint32_t* mask, const uint32_t* vmask,
+                      size_t n, const FilterScratch& sc, U* out, uint32_t* vout) {
+  const size_t tiles = filter_tiles(n);
+  const int smem = (int)sizeof(FilterTmaSmem<U>) + 128;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    AGPU_CUDA(cudaFuncSetAttribute(filter_scatter_tma_kernel<U, HAS_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  int per_sm = 0;
+  AGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_scatter_tma_kernel<U, HAS_V>, kBlock, smem));
+  if (per_sm < 1) per_sm = 1;
+  size_t grid = (size_t)dev->sm_count * per_sm;
+  if (grid > tiles) grid = tiles;
+  AGPU_LAUNCH(dev, (filter_scatter_tma_kernel<U, HAS_V>), (unsigned)grid, kBlock, smem, src, vsrc, mask, vmask, n, sc.counts,
+              sc.group_offsets, out, vout);
+  return agpu_finish_launch();
 }
 
 template <typename U>
@@ -461,13 +690,25 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
   const size_t tiles = filter_tiles(n);
   if (tiles > 0x7FFFFFFFull) return AGPU_EINVAL;
   if (!aligned16(src)) return AGPU_EINVAL;  // tile bases must be 16-byte aligned
+  constexpr int BLOCK = 256;  // measured: 128-thread CTAs (more resident tiles) are 2-6 % slower
+  // The TMA-staged persistent variant is kept for A/B profiling only: with 2 x 16 KiB row buffers
+  // + a 16 KiB stage only 4 CTAs fit per SM and it measured 4.9 ms vs 3.4 ms for this kernel's
+  // 8 independent CTAs per SM on 4 G rows at 10 % selectivity (profiles/r01_filter_variants.md).
+  static const bool use_tma = getenv("AGPU_FILTER_TMA") != nullptr;
+  if (use_tma) {
+    if (vsrc && vout) {
+      AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
+      return launch_filter_tma<U, true>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout);
+    }
+    return launch_filter_tma<U, false>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout);
+  }
   if (vsrc && vout) {
     AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
-    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true>), (unsigned)tiles, kBlock, 0, (const U*)src, vsrc, mask, vmask,
-                n, sc.counts, sc.group_offsets, (U*)out, vout);
+    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true, BLOCK>), (unsigned)tiles, BLOCK, 0, (const U*)src, vsrc, mask,
+                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
   } else {
-    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false>), (unsigned)tiles, kBlock, 0, (const U*)src, vsrc, mask, vmask,
-                n, sc.counts, sc.group_offsets, (U*)out, vout);
+    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)tiles, BLOCK, 0, (const U*)src, vsrc, mask,
+                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
   }
   return agpu_finish_launch();
 }
