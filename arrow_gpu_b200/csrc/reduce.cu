@@ -29,40 +29,55 @@ struct BroadcastOp {
 // (e0+e1)+(e2+e3) (levels s=1,2), a 5-step xor-butterfly adds lanes l and l^1, l^2 .. l^16
 // (levels s=4..64; a+b == b+a bit-for-bit, so every lane ends with the group's half sum) and
 // the two halves are added last (s=128).  Lanes past the end contribute 0 like the shader's
-// bounds check.
+// bounds check.  A warp owns 4 consecutive groups and issues their 8 loads before the first add.
 template <typename T>
-__device__ __forceinline__ T half_sum(const T* __restrict__ in, size_t base, size_t len, int lane) {
+__device__ __forceinline__ T butterfly(T e0, T e1, T e2, T e3) {
+  T s = (e0 + e1) + (e2 + e3);  // levels s = 1, 2
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) s = s + __shfl_xor_sync(0xFFFFFFFFu, s, off);  // levels 4 .. 64
+  return s;
+}
+
+// bounds-checked half group (ragged end / unaligned input)
+template <typename T>
+__device__ __forceinline__ T half_sum_checked(const T* __restrict__ in, size_t base, size_t len, int lane) {
   const size_t i = base + (size_t)lane * 4;
   T e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-  if (i + 3 < len && ((reinterpret_cast<uintptr_t>(in + i) & 15u) == 0)) {
-    const Vec<T, 4> v = ld_vec<T, 4>(in + i, 0);
-    e0 = v.e[0]; e1 = v.e[1]; e2 = v.e[2]; e3 = v.e[3];
-  } else {
-    if (i < len) e0 = in[i];
-    if (i + 1 < len) e1 = in[i + 1];
-    if (i + 2 < len) e2 = in[i + 2];
-    if (i + 3 < len) e3 = in[i + 3];
-  }
-  T s = (e0 + e1) + (e2 + e3);
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) s = s + __shfl_xor_sync(0xFFFFFFFFu, s, off);
-  return s;
+  if (i < len) e0 = in[i];
+  if (i + 1 < len) e1 = in[i + 1];
+  if (i + 2 < len) e2 = in[i + 2];
+  if (i + 3 < len) e3 = in[i + 3];
+  return butterfly(e0, e1, e2, e3);
 }
 
 template <typename T, int GROUPS_PER_WARP>
 __global__ void __launch_bounds__(kBlock) sum_pass_kernel(const T* __restrict__ in, const size_t len,
-                                                          T* __restrict__ out, const size_t groups) {
+                                                          T* __restrict__ out, const size_t groups, const int vec) {
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
   const size_t g0 = warp * GROUPS_PER_WARP;
+  if (g0 >= groups) return;
   T r[GROUPS_PER_WARP];
+  if (vec && (g0 + GROUPS_PER_WARP) * 256 <= len) {
+    // all 2*GROUPS_PER_WARP coalesced 16-byte loads of the warp are in flight before the first add
+    Vec<T, 4> v[GROUPS_PER_WARP][2];
 #pragma unroll
-  for (int k = 0; k < GROUPS_PER_WARP; ++k) {
-    const size_t g = g0 + k;
-    if (g < groups) {
-      const T lo = half_sum<T>(in, g * 256, len, lane);
-      const T hi = half_sum<T>(in, g * 256 + 128, len, lane);
-      r[k] = lo + hi;
+    for (int k = 0; k < GROUPS_PER_WARP; ++k) {
+      v[k][0] = ld_vec<T, 4>(in + (g0 + k) * 256, lane);
+      v[k][1] = ld_vec<T, 4>(in + (g0 + k) * 256 + 128, lane);
+    }
+#pragma unroll
+    for (int k = 0; k < GROUPS_PER_WARP; ++k) {
+      const T lo = butterfly(v[k][0].e[0], v[k][0].e[1], v[k][0].e[2], v[k][0].e[3]);
+      const T hi = butterfly(v[k][1].e[0], v[k][1].e[1], v[k][1].e[2], v[k][1].e[3]);
+      r[k] = lo + hi;  // level s = 128
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < GROUPS_PER_WARP; ++k) {
+      const size_t g = g0 + k;
+      r[k] = 0;
+      if (g < groups) r[k] = half_sum_checked<T>(in, g * 256, len, lane) + half_sum_checked<T>(in, g * 256 + 128, len, lane);
     }
   }
   if (lane == 0) {
@@ -94,7 +109,7 @@ int run_sum(agpu_device* dev, const T* a, size_t n, T* out_dev) {
     T* dst = groups == 1 ? out_dev : buf[which];
     const size_t warps = ceil_div(groups, (size_t)GPW);
     const size_t grid = ceil_div(warps, (size_t)(kBlock / 32));
-    AGPU_LAUNCH(dev, (sum_pass_kernel<T, GPW>), (unsigned)grid, kBlock, 0, in, len, dst, groups);
+    AGPU_LAUNCH(dev, (sum_pass_kernel<T, GPW>), (unsigned)grid, kBlock, 0, in, len, dst, groups, aligned16(in) ? 1 : 0);
     rc = agpu_finish_launch();
     if (rc || groups == 1) break;
     in = dst;

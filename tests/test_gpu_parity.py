@@ -342,3 +342,30 @@ def test_large_properties_i8(device):
     idx = np.arange(0, n, 9973)
     assert np.array_equal(s[idx], (x[idx].astype(np.int16) + y[idx]).astype(np.int8))
     assert int(gt.raw_values().sum()) == int((x > y).sum())
+
+
+def test_more_than_2_32_rows(device):
+    """64-bit row indexing: n = 2^32 + 77 int8 rows (4.3 GB per column).  add / gt / cast / filter are
+    checked against numpy over the whole column (bitmap bit indices and byte offsets exceed 32 bits)."""
+    n = (1 << 32) + 77
+    rng = np.random.default_rng(77)
+    x = rng.integers(-128, 128, n, dtype=np.int8)
+    y = np.roll(x, 12345)          # a second column without another RNG pass
+    a, b = ag.Int8ArrayGPU.from_numpy(x, None, device), ag.Int8ArrayGPU.from_numpy(y, None, device)
+    s = a.add(b).raw_values()
+    assert np.array_equal(s[-(1 << 20):], (x[-(1 << 20):].astype(np.int16) + y[-(1 << 20):]).astype(np.int8))
+    assert np.array_equal(s[:: 65537], (x[:: 65537].astype(np.int16) + y[:: 65537]).astype(np.int8))
+    del s
+    g = a.gt(b)
+    bits = np.unpackbits(device.retrive_data(g.data, O.words(n) * 4), bitorder="little")[:n].view(bool)
+    want = x > y
+    assert np.array_equal(bits[-(1 << 20):], want[-(1 << 20):])
+    assert int(bits.sum()) == int(want.sum())
+    # keep ~0.1 % of the rows, including the very last one
+    keep = (x == 127) & (y > 100)
+    keep[-1] = True
+    m = ag.BooleanArrayGPU(device.create_gpu_buffer_with_data(np.packbits(keep, bitorder="little")), device, n, None)
+    out = a.filter(m).raw_values()
+    assert np.array_equal(out, x[keep])
+    tail = ag.Int8ArrayGPU(ag.ArrowGpuBuffer(device, a.data.ptr + (1 << 32), 77, owned=False), device, 77, None)
+    assert np.array_equal(tail.cast(ag.Int32ArrayGPU).raw_values(), x[1 << 32:].astype(np.int32))
