@@ -64,6 +64,12 @@ SIGNATURES = {
     "agpu_filter_scratch_bytes": (_sz, [_sz]),
     "agpu_filter_count": (_i, [_p, _u32p, _u32p, _sz, _p, _p]),
     "agpu_filter_scatter": (_i, [_p, _i, _p, _u32p, _u32p, _u32p, _sz, _p, _p, _u32p]),
+    "agpu_ipc_alloc": (_i, [_p, _sz, C.POINTER(_p)]),
+    "agpu_ipc_free": (_i, [_p, _p]),
+    "agpu_ipc_export": (_i, [_p, _p, C.c_char_p]),
+    "agpu_ipc_open": (_i, [_p, C.c_char_p, C.POINTER(_p)]),
+    "agpu_ipc_close": (_i, [_p, _p]),
+    "agpu_take_sharded": (_i, [_p, _i, _i, C.POINTER(_p), C.POINTER(_p), C.POINTER(C.c_uint64), _u32p, _p, _sz, _u32p]),
     "agpu_broadcast": (_i, [_p, _i, _p, _p, _sz]),
     "agpu_sum": (_i, [_p, _i, _p, _sz, _p]),
     "agpu_any": (_i, [_p, _u32p, _sz, _u32p]),

@@ -126,6 +126,27 @@ class GpuDevice:
         """gpu_device.rs:203-210"""
         return self.create_gpu_buffer_with_data(np.asarray([value]))
 
+    def create_ipc_buffer_with_data(self, data: np.ndarray) -> "ArrowGpuBuffer":
+        """like create_gpu_buffer_with_data but in memory other GPUs of the box can map (CUDA IPC)"""
+        data = np.ascontiguousarray(data)
+        p = C.c_void_p()
+        check(lib().agpu_ipc_alloc(self.handle, _round_up(max(data.nbytes, 1), 16), C.byref(p)), "agpu_ipc_alloc")
+        buf = ArrowGpuBuffer(self, p.value, data.nbytes, kind="ipc")
+        if data.nbytes:
+            check(lib().agpu_h2d(self.handle, buf.ptr, data.ctypes.data, data.nbytes), "agpu_h2d")
+            check(lib().agpu_sync(self.handle), "agpu_sync")
+        return buf
+
+    def ipc_export(self, buffer: "ArrowGpuBuffer") -> bytes:
+        h = C.create_string_buffer(64)
+        check(lib().agpu_ipc_export(self.handle, buffer.ptr, h), "agpu_ipc_export")
+        return h.raw
+
+    def ipc_open(self, handle: bytes, size: int) -> "ArrowGpuBuffer":
+        p = C.c_void_p()
+        check(lib().agpu_ipc_open(self.handle, handle, C.byref(p)), "agpu_ipc_open")
+        return ArrowGpuBuffer(self, p.value, size, kind="peer")
+
     def clone_buffer(self, buffer: "ArrowGpuBuffer") -> "ArrowGpuBuffer":
         """gpu_device.rs:212-222"""
         out = self.create_empty_buffer(buffer.size)
@@ -185,10 +206,12 @@ class GpuEvent:
 class ArrowGpuBuffer:
     """array/buffer.rs:5-7 — owns one device allocation; dropping it frees stream-ordered."""
 
-    __slots__ = ("device", "ptr", "_size", "_owned", "__weakref__")
+    __slots__ = ("device", "ptr", "_size", "_owned", "_kind", "__weakref__")
 
-    def __init__(self, device: GpuDevice, ptr: int, size: int, owned: bool = True):
-        self.device, self.ptr, self._size, self._owned = device, ptr, size, owned
+    def __init__(self, device: GpuDevice, ptr: int, size: int, owned: bool = True, kind: str = "pool"):
+        # kind: "pool" = stream-ordered pool allocation; "ipc" = cudaMalloc'd, exportable to the
+        # other GPUs of the box; "peer" = another process's buffer opened through CUDA IPC
+        self.device, self.ptr, self._size, self._owned, self._kind = device, ptr, size, owned, kind
 
     @property
     def size(self) -> int:
@@ -198,7 +221,12 @@ class ArrowGpuBuffer:
     def __del__(self):
         try:
             if self._owned and self.ptr and self.device.handle:
-                lib().agpu_free(self.device.handle, self.ptr)
+                if self._kind == "ipc":
+                    lib().agpu_ipc_free(self.device.handle, self.ptr)
+                elif self._kind == "peer":
+                    lib().agpu_ipc_close(self.device.handle, self.ptr)
+                else:
+                    lib().agpu_free(self.device.handle, self.ptr)
         except Exception:
             pass
         self.ptr = None

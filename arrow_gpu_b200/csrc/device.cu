@@ -191,3 +191,48 @@ extern "C" int agpu_event_elapsed_ms(agpu_event* start, agpu_event* stop, float*
   AGPU_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
   return 0;
 }
+
+// ---- CUDA IPC: shards visible to the other GPUs of the box (peer memory over NVLink) ----
+extern "C" int agpu_ipc_alloc(agpu_device* dev, size_t bytes, void** out) {
+  if (!dev) return AGPU_ENODEVICE;
+  AGPU_REQUIRE(out);
+  AGPU_CUDA(cudaSetDevice(dev->ordinal));
+  AGPU_CUDA(cudaMalloc(out, bytes ? bytes : 16));
+  return 0;
+}
+
+extern "C" int agpu_ipc_free(agpu_device* dev, void* ptr) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!ptr) return 0;
+  AGPU_CUDA(cudaStreamSynchronize(dev->stream));
+  AGPU_CUDA(cudaFree(ptr));
+  return 0;
+}
+
+extern "C" int agpu_ipc_export(agpu_device* dev, const void* ptr, unsigned char handle[AGPU_IPC_HANDLE_BYTES]) {
+  if (!dev) return AGPU_ENODEVICE;
+  AGPU_REQUIRE(ptr && handle);
+  static_assert(sizeof(cudaIpcMemHandle_t) == AGPU_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  AGPU_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+  memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+
+extern "C" int agpu_ipc_open(agpu_device* dev, const unsigned char handle[AGPU_IPC_HANDLE_BYTES], void** out) {
+  if (!dev) return AGPU_ENODEVICE;
+  AGPU_REQUIRE(handle && out);
+  AGPU_CUDA(cudaSetDevice(dev->ordinal));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  AGPU_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int agpu_ipc_close(agpu_device* dev, void* ptr) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!ptr) return 0;
+  AGPU_CUDA(cudaStreamSynchronize(dev->stream));
+  AGPU_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}

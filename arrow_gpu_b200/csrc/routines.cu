@@ -176,6 +176,77 @@ int run_take(agpu_device* dev, const void* src, size_t src_len, const uint32_t* 
 }
 
 // ============================================================================================
+// take with GLOBAL row indices over row-range shards
+// ============================================================================================
+// Each shard pointer is local memory or another GPU's memory opened through CUDA IPC; the gather
+// loads go straight over NVLink/NVSwitch.  Same granule scheme as TakeOp: 4 indices per lane as
+// one 16-byte chunk, 4 gathers, one chunk store; validity bits with the compare shuffle network.
+struct ShardTable {
+  const void* values[AGPU_MAX_SHARDS];
+  const uint32_t* validity[AGPU_MAX_SHARDS];
+  unsigned long long begin[AGPU_MAX_SHARDS + 1];
+  int n;
+  int has_validity;
+};
+
+template <typename U>
+struct TakeShardedOp {
+  static constexpr int G = 4;
+  ShardTable t;
+  const uint32_t* idx;
+  U* out;
+  struct In { Vec<uint32_t, 4> i; };
+  __device__ __forceinline__ int shard_of(uint32_t r) const {
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < AGPU_MAX_SHARDS; ++k) s += (k < t.n && r >= t.begin[k]) ? 1 : 0;
+    return s;
+  }
+  __device__ __forceinline__ U fetch(uint32_t r, uint32_t& vbit) const {
+    vbit = 0;
+    if (r >= t.begin[t.n]) return (U)0;
+    const int s = shard_of(r);
+    const uint64_t local = r - t.begin[s];
+    if (t.has_validity) {
+      const uint32_t* v = t.validity[s];
+      vbit = v ? (v[local >> 5] >> (local & 31)) & 1u : 1u;
+    }
+    return static_cast<const U*>(t.values[s])[local];
+  }
+  __device__ __forceinline__ In load(size_t g) const { return In{ld_vec<uint32_t, 4>(idx, g)}; }
+  // BitsOp interface (values are stored as a side effect, validity bits returned)
+  __device__ __forceinline__ uint32_t bits(size_t g, const In& in) const {
+    Vec<U, 4> o;
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t vb;
+      o.e[k] = fetch(in.i.e[k], vb);
+      m |= vb << k;
+    }
+    st_vec<U, 4>(out, g, o);
+    return m;
+  }
+  __device__ __forceinline__ bool bit_at(size_t j) const {
+    uint32_t vb;
+    out[j] = fetch(idx[j], vb);
+    return vb;
+  }
+  // ew Op interface (no validity)
+  __device__ __forceinline__ void run(size_t g, const In& in) const { (void)bits(g, in); }
+  __device__ __forceinline__ void tail(size_t j) const { (void)bit_at(j); }
+};
+
+template <typename U>
+int run_take_sharded(agpu_device* dev, const ShardTable& t, const uint32_t* idx, void* out, size_t m, uint32_t* vout) {
+  TakeShardedOp<U> op{t, idx, (U*)out};
+  BmAnd none{};
+  const bool al = aligned16(idx) && aligned16(out);
+  if (t.has_validity && vout) return launch_bits(dev, op, vout, m, none, al);
+  return launch_ew(dev, op, m, none, al);
+}
+
+// ============================================================================================
 // put: routines/compute_shaders/32bit/put.wgsl:17-23, bool/put.wgsl:17-34
 // ============================================================================================
 template <typename U>
@@ -809,6 +880,33 @@ extern "C" int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src,
     case 4: return run_filter<uint32_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
     case 2: return run_filter<uint16_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
     case 1: return run_filter<uint8_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
+    default: return AGPU_EUNSUPPORTED;
+  }
+}
+
+extern "C" int agpu_take_sharded(agpu_device* dev, int dtype, int n_shards, const void* const* shard_values,
+                                 const uint32_t* const* shard_validity, const uint64_t* shard_begin,
+                                 const uint32_t* idx, void* out, size_t m, uint32_t* vout) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (n_shards < 1 || n_shards > AGPU_MAX_SHARDS || !shard_values || !shard_begin) return AGPU_EINVAL;
+  if (m && (!idx || !out)) return AGPU_EINVAL;
+  if (m == 0) return 0;
+  ShardTable t{};
+  t.n = n_shards;
+  t.has_validity = 0;
+  for (int s = 0; s < n_shards; ++s) {
+    t.values[s] = shard_values[s];
+    t.validity[s] = shard_validity ? shard_validity[s] : nullptr;
+    if (t.validity[s]) t.has_validity = 1;
+    t.begin[s] = shard_begin[s];
+    if (shard_begin[s + 1] > shard_begin[s] && !shard_values[s]) return AGPU_EINVAL;
+  }
+  t.begin[n_shards] = shard_begin[n_shards];
+  if (vout && !t.has_validity) return AGPU_EINVAL;
+  switch (agpu_dtype_size(dtype)) {
+    case 4: return run_take_sharded<uint32_t>(dev, t, idx, out, m, vout);
+    case 2: return run_take_sharded<uint16_t>(dev, t, idx, out, m, vout);
+    case 1: return run_take_sharded<uint8_t>(dev, t, idx, out, m, vout);
     default: return AGPU_EUNSUPPORTED;
   }
 }

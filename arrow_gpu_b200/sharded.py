@@ -115,3 +115,86 @@ def sharded_filter(array, mask):
     out = array.filter_scatter_op(plan, int(counts[rank]), pipeline)
     pipeline.finish()
     return out, offsets[rank], total
+
+
+class ShardedColumn:
+    """One column split into contiguous row ranges, one shard per rank/GPU, with every shard
+    mapped into every process (CUDA IPC) so kernels can read peer shards directly over NVLink.
+
+    `take_global(indexes)` gathers rows by GLOBAL row number: one kernel, no request/response
+    exchange (the reference has neither sharding nor a global take)."""
+
+    def __init__(self, array_cls, values, valid, n_total: int, device):
+        """values/valid: this rank's shard (numpy) of a column of n_total rows"""
+        import numpy as np
+        from .array import NullBitBufferGpu, pack_bits
+        dist = _dist()
+        self.rank = dist.get_rank() if dist else 0
+        self.world = dist.get_world_size() if dist else 1
+        self.cls, self.device, self.n_total = array_cls, device, n_total
+        self.begin = [row_range(n_total, r, self.world)[0] for r in range(self.world)] + [n_total]
+        assert len(values) == self.begin[self.rank + 1] - self.begin[self.rank]
+        if isinstance(values, array_cls):      # an existing device array: copy it into exportable memory
+            src, rows = values, values.len
+            data = self._ipc_copy(device, src.data, rows * array_cls.NP.itemsize)
+            nb = None
+            if src.null_buffer is not None:
+                nb = NullBitBufferGpu(self._ipc_copy(device, src.null_buffer.bit_buffer, (rows + 31) // 32 * 4), rows, device)
+        else:
+            rows = len(values)
+            data = device.create_ipc_buffer_with_data(np.ascontiguousarray(values.astype(array_cls.NP, copy=False)))
+            nb = None
+            if valid is not None:
+                nb = NullBitBufferGpu(device.create_ipc_buffer_with_data(pack_bits(valid)), rows, device)
+        self.local = array_cls(data, device, rows, nb)
+        # exchange (handle, has_validity) with every rank and map the peers' shards
+        mine = (device.ipc_export(data), device.ipc_export(nb.bit_buffer) if nb is not None else None)
+        everyone = [mine]
+        if dist:
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine)
+        self.values, self.validity = [], []
+        for r, (vh, bh) in enumerate(everyone):
+            rows = self.begin[r + 1] - self.begin[r]
+            if r == self.rank:
+                self.values.append(data)
+                self.validity.append(nb.bit_buffer if nb is not None else None)
+            else:
+                self.values.append(device.ipc_open(vh, rows * array_cls.NP.itemsize) if rows else None)
+                self.validity.append(device.ipc_open(bh, (rows + 31) // 32 * 4) if (bh is not None and rows) else None)
+        self.has_validity = any(v is not None for v in self.validity)
+
+    @staticmethod
+    def _ipc_copy(device, buffer, nbytes):
+        import ctypes as C
+        from ._ffi import check, lib
+        from .array import ArrowGpuBuffer
+        p = C.c_void_p()
+        check(lib().agpu_ipc_alloc(device.handle, max(nbytes, 16), C.byref(p)), "agpu_ipc_alloc")
+        out = ArrowGpuBuffer(device, p.value, nbytes, kind="ipc")
+        check(lib().agpu_d2d(device.handle, out.ptr, buffer.ptr, nbytes), "agpu_d2d")
+        device.sync()
+        return out
+
+    def take_global(self, indexes):
+        """out[j] = column[indexes[j]] for this rank's (local) UInt32 index array"""
+        import ctypes as C
+        from ._ffi import check, lib
+        from .array import NullBitBufferGpu, bitmap_words
+        dev, m = self.device, indexes.len
+        vals = (C.c_void_p * self.world)(*[b.ptr if b is not None else None for b in self.values])
+        bits = (C.c_void_p * self.world)(*[b.ptr if b is not None else None for b in self.validity])
+        begin = (C.c_uint64 * (self.world + 1))(*self.begin)
+        nb = None
+        if self.has_validity:
+            nb = NullBitBufferGpu(dev.create_empty_buffer(bitmap_words(m) * 4), m, dev)
+        out = self.cls.empty(m, dev, nb)
+        check(lib().agpu_take_sharded(dev.handle, self.cls.DTYPE, self.world, vals, bits if self.has_validity else None,
+                                      begin, indexes.data.ptr, out.data.ptr, m, nb.bit_buffer.ptr if nb else None),
+              "take_sharded")
+        return out
+
+    def close(self):
+        """unmap the peers' shards (after a barrier: nobody may still be reading ours)"""
+        barrier()
+        self.values, self.validity = [], []

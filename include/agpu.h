@@ -246,6 +246,27 @@ int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src, const uint
 
 /* ---- "next" rows ---- */
 
+/* Global-index take across the row-range shards of one column (8f rank 2): every process owns
+ * one shard; shards are made visible to the other GPUs of the box through CUDA IPC and the
+ * gather kernel reads them directly over NVLink/NVSwitch peer memory — no all-to-all of
+ * requests and replies.  Exportable buffers come from cudaMalloc (pool memory cannot be
+ * exported). */
+#define AGPU_IPC_HANDLE_BYTES 64
+#define AGPU_MAX_SHARDS 16
+int agpu_ipc_alloc(agpu_device* dev, size_t bytes, void** out);
+int agpu_ipc_free(agpu_device* dev, void* ptr);
+int agpu_ipc_export(agpu_device* dev, const void* ptr, unsigned char handle[AGPU_IPC_HANDLE_BYTES]);
+int agpu_ipc_open(agpu_device* dev, const unsigned char handle[AGPU_IPC_HANDLE_BYTES], void** out);
+int agpu_ipc_close(agpu_device* dev, void* ptr);
+/* out[j] = column[idx[j]] where global row r lives in shard s with shard_begin[s] <= r <
+ * shard_begin[s+1] at shard_values[s][r - shard_begin[s]] (local or peer device memory).
+ * shard_validity may be NULL (no shard has a bitmap) or hold one bitmap pointer (or NULL = all
+ * valid) per shard; vout receives the gathered validity bits.  Rows >= shard_begin[n_shards]
+ * read as zero.  All arrays of pointers/offsets are HOST arrays of n_shards (+1) entries. */
+int agpu_take_sharded(agpu_device* dev, int dtype, int n_shards, const void* const* shard_values,
+                      const uint32_t* const* shard_validity, const uint64_t* shard_begin,
+                      const uint32_t* idx, void* out, size_t m, uint32_t* vout);
+
 /* Broadcast::broadcast_op, array/src/kernels/broadcast.rs:6-17, */
 /* array/compute_shaders/{f32,i32,u32}/broadcast.wgsl: out[i] = *scalar_host (by value bits) */
 int agpu_broadcast(agpu_device* dev, int dtype, const void* scalar_host, void* out, size_t n);

@@ -56,6 +56,18 @@ def main():
     t[offset:offset + len(got)] = torch.from_numpy(got).to(t.device)
     dist.all_reduce(t)
     assert np.array_equal(t[:total].cpu().numpy(), want)
+    # global-index take over peer memory (CUDA IPC + NVLink loads inside the gather kernel)
+    col = sharded.ShardedColumn(ag.Int32ArrayGPU, vals[b:e], valid[b:e], n, dev)
+    gidx = np.random.default_rng(1000 + rank).integers(0, n, 200_003).astype(np.uint32)
+    gidx[:3] = [0, n - 1, n + 5]                     # first row, last row, out of range (reads 0)
+    taken = col.take_global(ag.UInt32ArrayGPU.from_numpy(gidx, None, dev))
+    safe = np.minimum(gidx, n - 1)
+    want_vals = np.where(gidx < n, vals[safe], 0)
+    want_valid = np.where(gidx < n, valid[safe], False)
+    assert np.array_equal(taken.raw_values(), want_vals)
+    assert np.array_equal(taken.null_buffer.flags(), want_valid)
+    col.close()
+    del col
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU check ok: world={world}, {total} of {n} rows kept")
