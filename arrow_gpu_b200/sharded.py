@@ -84,6 +84,9 @@ def barrier() -> None:
         dist.barrier()
 
 
+_EXCHANGE_CTX: dict = {}
+
+
 def sharded_filter(array, mask):
     """Filter this rank's shard and learn where its output sits in the global result:
     returns (local filtered array, global offset of its first row, global row count).
@@ -102,15 +105,23 @@ def sharded_filter(array, mask):
     import torch
     from .array import ArrowComputePipeline
     dev = array.gpu_device
-    tdev = torch.device("cuda", dev.ordinal)
     rank, world = dist.get_rank(), dist.get_world_size()
-    with torch.cuda.stream(torch.cuda.ExternalStream(dev.stream_ptr, device=tdev)):
-        mine = torch.zeros(1, dtype=torch.int64, device=tdev)
+    ctx = _EXCHANGE_CTX.get(id(dev))
+    if ctx is None:   # per device handle: its stream as a torch stream + reusable count buffers
+        tdev = torch.device("cuda", dev.ordinal)
+        ctx = (torch.cuda.ExternalStream(dev.stream_ptr, device=tdev),
+               torch.zeros(1, dtype=torch.int64, device=tdev), torch.zeros(world, dtype=torch.int64, device=tdev),
+               torch.zeros(world, dtype=torch.int64).pin_memory())
+        torch.cuda.synchronize(tdev)
+        _EXCHANGE_CTX[id(dev)] = ctx
+    ext, mine, gathered, host = ctx
+    with torch.cuda.stream(ext):
         pipeline = ArrowComputePipeline(dev, "sharded_filter")
         plan = array.filter_count_op(mask, pipeline, total_ptr=mine.data_ptr())
-        gathered = torch.empty(world, dtype=torch.int64, device=tdev)
         dist.all_gather_into_tensor(gathered, mine)
-        counts = gathered.cpu().tolist()          # the one synchronisation
+        host.copy_(gathered, non_blocking=True)
+        ext.synchronize()                         # the one synchronisation
+        counts = host.tolist()
     offsets, total = exclusive_offsets(counts)
     out = array.filter_scatter_op(plan, int(counts[rank]), pipeline)
     pipeline.finish()
