@@ -76,6 +76,18 @@ SIGNATURES = {
     "agpu_all": (_i, [_p, _u32p, _sz, _u32p]),
 }
 
+
+
+class ChainStep(C.Structure):
+    """agpu_chain_step"""
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("operand", C.c_void_p), ("validity", C.c_void_p),
+                ("scalar", C.c_float)]
+
+
+STEP_UNARY, STEP_BINARY_COLUMN, STEP_BINARY_SCALAR, STEP_COMPARE_COLUMN, STEP_COMPARE_SCALAR = range(5)
+CHAIN_MAX_STEPS = 8
+SIGNATURES["agpu_fused_chain"] = (_i, [_p, _i, _p, _u32p, C.POINTER(ChainStep), _i, _p, _sz, _u32p])
+
 _lib = None
 
 

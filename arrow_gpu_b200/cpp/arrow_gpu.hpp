@@ -548,4 +548,49 @@ inline BooleanArrayGPU fused_mul_add_gt(const Float32ArrayGPU& a, const Float32A
   return out;
 }
 
+// general fused linear chain (agpu_fused_chain): acc = f32(a); each step is unary(op), binary(op,
+// column | scalar) or a final compare -> BooleanArrayGPU.  Bit-identical to the unfused ops.
+struct ChainStep {
+  agpu_chain_step raw{};
+  static ChainStep unary(agpu_unop op) { ChainStep s; s.raw.kind = AGPU_STEP_UNARY; s.raw.op = op; return s; }
+  static ChainStep binary(agpu_binop op, const Float32ArrayGPU& col) {
+    ChainStep s; s.raw.kind = AGPU_STEP_BINARY_COLUMN; s.raw.op = op; s.raw.operand = (const float*)col.data->ptr();
+    s.raw.validity = vptr(col.null_buffer); s.has_validity = bool(col.null_buffer); return s;
+  }
+  static ChainStep binary(agpu_binop op, float scalar) { ChainStep s; s.raw.kind = AGPU_STEP_BINARY_SCALAR; s.raw.op = op; s.raw.scalar = scalar; return s; }
+  static ChainStep compare(agpu_cmpop op, const Float32ArrayGPU& col) {
+    ChainStep s; s.raw.kind = AGPU_STEP_COMPARE_COLUMN; s.raw.op = op; s.raw.operand = (const float*)col.data->ptr();
+    s.raw.validity = vptr(col.null_buffer); s.has_validity = bool(col.null_buffer); return s;
+  }
+  static ChainStep compare(agpu_cmpop op, float scalar) { ChainStep s; s.raw.kind = AGPU_STEP_COMPARE_SCALAR; s.raw.op = op; s.raw.scalar = scalar; return s; }
+  bool has_validity = false;
+};
+
+template <typename T>
+std::variant<Float32ArrayGPU, BooleanArrayGPU> fused_chain(const PrimitiveArrayGpu<T>& a, const std::vector<ChainStep>& steps) {
+  std::vector<agpu_chain_step> raw;
+  bool any_validity = bool(a.null_buffer), pred = false;
+  for (const auto& s : steps) {
+    raw.push_back(s.raw);
+    any_validity = any_validity || s.has_validity;
+    pred = s.raw.kind == AGPU_STEP_COMPARE_COLUMN || s.raw.kind == AGPU_STEP_COMPARE_SCALAR;
+  }
+  Validity nb;
+  if (any_validity) nb = NullBitBufferGpu{std::make_shared<ArrowGpuBuffer>(a.gpu_device, bitmap_words(a.len) * 4), a.len, a.gpu_device};
+  if (pred) {
+    auto out = BooleanArrayGPU::empty(a.len, a.gpu_device, nb);
+    int rc = agpu_fused_chain(a.gpu_device->handle(), PrimitiveArrayGpu<T>::DTYPE, a.data->ptr(), vptr(a.null_buffer), raw.data(),
+                              (int)raw.size(), out.data->ptr(), a.len, vptr_mut(out.null_buffer));
+    if (rc == AGPU_EUNSUPPORTED || rc == AGPU_EINVAL) throw Panic("fused_chain: unsupported chain");
+    check(rc, "fused_chain");
+    return out;
+  }
+  auto out = Float32ArrayGPU::empty(a.len, a.gpu_device, nb);
+  int rc = agpu_fused_chain(a.gpu_device->handle(), PrimitiveArrayGpu<T>::DTYPE, a.data->ptr(), vptr(a.null_buffer), raw.data(),
+                            (int)raw.size(), out.data->ptr(), a.len, vptr_mut(out.null_buffer));
+  if (rc == AGPU_EUNSUPPORTED || rc == AGPU_EINVAL) throw Panic("fused_chain: unsupported chain");
+  check(rc, "fused_chain");
+  return out;
+}
+
 }  // namespace arrow_gpu

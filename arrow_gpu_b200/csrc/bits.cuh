@@ -8,6 +8,7 @@
 // A BitsOp provides: G, In, load(g), bits(g, In) -> low G bits, bit_at(i) -> one row's predicate.
 #pragma once
 #include "common.cuh"
+#include "elementwise.cuh"
 
 template <int S>
 __device__ __forceinline__ uint32_t merge_bit_groups(uint32_t v) {
@@ -31,9 +32,16 @@ __global__ void __launch_bounds__(kBlock) bits_kernel(const Op op, uint32_t* __r
     typename Op::In in[UNROLL];
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) in[j] = op.load(g0 + (size_t)j * kBlock);
+    uint32_t b[UNROLL];
+    if constexpr (IsJointOp<Op>::value) {
+      op.template bits_joint<UNROLL>(g0, in, b);
+    } else {
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) b[j] = op.bits(g0 + (size_t)j * kBlock, in[j]);
+    }
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) {
-      const uint32_t w = merge_bit_groups<S>(op.bits(g0 + (size_t)j * kBlock, in[j]) << shift);
+      const uint32_t w = merge_bit_groups<S>(b[j] << shift);
       if (lane % S == 0) out[(g0 + (size_t)j * kBlock) / S] = w;
     }
   } else {

@@ -19,7 +19,14 @@
 //   void run(size_t g, const In&) const;   compute + streaming store of granule g
 //   void tail(size_t i) const;       one row, element-wise (leftover rows / unaligned buffers)
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
+
+// Ops whose per-granule work has a fixed dispatch cost (the chain interpreter) set
+// `static constexpr bool JOINT = true` and get all UNROLL granules of a full tile in one call.
+template <class Op, class = void> struct IsJointOp : std::false_type {};
+template <class Op> struct IsJointOp<Op, std::void_t<decltype(Op::JOINT)>> : std::bool_constant<Op::JOINT> {};
 
 template <class Op, int UNROLL, class Bm>
 __global__ void __launch_bounds__(kBlock) ew_kernel(const Op op, const size_t n, const Bm bm) {
@@ -31,8 +38,12 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Op op, const size_t n,
     typename Op::In in[UNROLL];
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) in[j] = op.load(g0 + (size_t)j * kBlock);
+    if constexpr (IsJointOp<Op>::value) {
+      op.template run_joint<UNROLL>(g0, in);  // granule j sits at g0 + j*kBlock
+    } else {
 #pragma unroll
-    for (int j = 0; j < UNROLL; ++j) op.run(g0 + (size_t)j * kBlock, in[j]);
+      for (int j = 0; j < UNROLL; ++j) op.run(g0 + (size_t)j * kBlock, in[j]);
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) {

@@ -684,6 +684,70 @@ def fused_mul_add_gt(a, b, c, d) -> BooleanArrayGPU:
 
 
 # ==========================================================================================
+# general fused linear chains (north_star (2)): one kernel for  cast -> op -> op -> ... [-> compare]
+# ==========================================================================================
+_CHAIN_UNARY = {"neg": _ffi.NEG, "abs": _ffi.ABS, "sqrt": _ffi.SQRT, "cbrt": _ffi.CBRT, "exp": _ffi.EXP,
+                "exp2": _ffi.EXP2, "log": _ffi.LOG, "log2": _ffi.LOG2, "sin": _ffi.SIN, "cos": _ffi.COS,
+                "acos": _ffi.ACOS, "sinh": _ffi.SINH}
+_CHAIN_BINARY = {"add": _ffi.ADD, "sub": _ffi.SUB, "mul": _ffi.MUL, "div": _ffi.DIV, "rem": _ffi.REM,
+                 "min": _ffi.MIN, "max": _ffi.MAX, "power": _ffi.POW}
+_CHAIN_COMPARE = {"gt": _ffi.GT, "gteq": _ffi.GTEQ, "lt": _ffi.LT, "lteq": _ffi.LTEQ, "eq": _ffi.EQ}
+_CHAIN_INPUT = (Float32ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU, Int16ArrayGPU, UInt16ArrayGPU)
+
+
+def fused_chain_op(data, steps, pipeline):
+    """Evaluate a linear chain in ONE kernel.  `steps` is a list of
+         ("sqrt",)                 unary f32 op on the running value
+         ("mul", other)            binary op with a Float32ArrayGPU column or a python float
+         ("gt", other)             compare (only as the last step) -> BooleanArrayGPU
+    The running value starts as cast<f32>(data) (f32, i8, u8, i16 or u16 column).  The result is
+    bit-identical to applying the same `*_op`s one after another on a pipeline; validity is the AND
+    of all columns' bitmaps.  Example: fused_chain(a, [("mul", b), ("add", c), ("gt", d)])."""
+    if not isinstance(data, _CHAIN_INPUT):
+        raise Panic(f"fused_chain not supported for type {data.get_dtype()}")
+    if not 1 <= len(steps) <= _ffi.CHAIN_MAX_STEPS:
+        raise Panic(f"fused_chain takes 1..{_ffi.CHAIN_MAX_STEPS} steps")
+    arr = (_ffi.ChainStep * len(steps))()
+    validities = [data.null_buffer]
+    is_pred = False
+    for k, step in enumerate(steps):
+        name, operand = step[0], (step[1] if len(step) > 1 else None)
+        if name in _CHAIN_UNARY and operand is None:
+            arr[k].kind, arr[k].op = _ffi.STEP_UNARY, _CHAIN_UNARY[name]
+            continue
+        if name in _CHAIN_BINARY:
+            op, kinds = _CHAIN_BINARY[name], (_ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_SCALAR)
+        elif name in _CHAIN_COMPARE:
+            if k != len(steps) - 1:
+                raise Panic("a compare can only end a fused chain")
+            op, kinds, is_pred = _CHAIN_COMPARE[name], (_ffi.STEP_COMPARE_COLUMN, _ffi.STEP_COMPARE_SCALAR), True
+        else:
+            raise Panic(f"fused_chain: unknown step {step!r}")
+        arr[k].op = op
+        if isinstance(operand, Float32ArrayGPU):
+            _check_same_len(data, operand, "fused_chain")
+            arr[k].kind, arr[k].operand, arr[k].validity = kinds[0], operand.data.ptr, _vptr(operand.null_buffer)
+            validities.append(operand.null_buffer)
+        elif isinstance(operand, (int, float, np.floating, np.integer)):
+            arr[k].kind, arr[k].scalar = kinds[1], float(operand)
+        else:
+            raise Panic(f"fused_chain: operand of {name!r} must be a Float32ArrayGPU or a number")
+    dev = data.gpu_device
+    nb = _new_validity(dev, data.len, *validities)
+    out = (BooleanArrayGPU if is_pred else Float32ArrayGPU).empty(data.len, dev, nb)
+    check(lib().agpu_fused_chain(dev.handle, data.DTYPE, data.data.ptr, _vptr(data.null_buffer), arr, len(steps),
+                                 out.data.ptr, data.len, _vptr(nb)), "fused_chain")
+    return out
+
+
+def fused_chain(data, steps):
+    pipeline = _pipeline_for(data)
+    out = fused_chain_op(data, steps, pipeline)
+    pipeline.finish()
+    return out
+
+
+# ==========================================================================================
 # profiling hook (the reference's `profile` feature, gpu_utils/compute_query.rs): every `*_op`
 # recorded on a pipeline created with profile=True is bracketed by a CUDA event pair
 # ==========================================================================================

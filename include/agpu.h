@@ -206,6 +206,37 @@ int agpu_fused_mul_add_gt(agpu_device* dev, const float* a, const float* b, cons
                           const uint32_t* vb, const uint32_t* vc, const uint32_t* vd,
                           uint32_t* vout);
 
+/* ---- general fused LINEAR chains on f32 (north_star (2): "cast and f32 math/trig are fused where
+ * chained") ----
+ * acc = f32(in[i]); then for each step, in order:
+ *   AGPU_STEP_UNARY          acc = unop(acc)                 (NEG ABS SQRT CBRT EXP EXP2 LOG LOG2 SIN COS ACOS SINH)
+ *   AGPU_STEP_BINARY_COLUMN  acc = acc binop operand[i]      (ADD SUB MUL DIV REM MIN MAX POW; operand = f32 column)
+ *   AGPU_STEP_BINARY_SCALAR  acc = acc binop scalar
+ *   AGPU_STEP_COMPARE_COLUMN / _SCALAR   bit = acc cmpop rhs (only as the LAST step; out is then a bitmap)
+ * Every step rounds exactly like the stand-alone kernel of that op, so a fused chain is
+ * bit-identical to the same ops recorded one by one on an ArrowComputePipeline
+ * (crates/arrow/examples/simple.rs:45-72) — it just reads each input once and writes one output.
+ * in_dtype: F32, I8, U8, I16, U16 (the int->f32 cast is fused like trigonometry/compute_shaders/
+ * {i8,u8,i16,u16}).  At most AGPU_CHAIN_MAX_STEPS steps and 3 operand columns.  vout = AND of
+ * the validity bitmaps of the input and of the operand columns (NULL = all valid). */
+#define AGPU_CHAIN_MAX_STEPS 8
+typedef enum {
+  AGPU_STEP_UNARY = 0,
+  AGPU_STEP_BINARY_COLUMN = 1,
+  AGPU_STEP_BINARY_SCALAR = 2,
+  AGPU_STEP_COMPARE_COLUMN = 3,
+  AGPU_STEP_COMPARE_SCALAR = 4
+} agpu_step_kind;
+typedef struct {
+  int32_t kind;             /* agpu_step_kind */
+  int32_t op;               /* agpu_unop / agpu_binop / agpu_cmpop id */
+  const float* operand;     /* device f32 column for *_COLUMN steps */
+  const uint32_t* validity; /* its validity bitmap or NULL */
+  float scalar;             /* immediate for *_SCALAR steps */
+} agpu_chain_step;
+int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, const uint32_t* vin,
+                     const agpu_chain_step* steps, int n_steps, void* out, size_t n, uint32_t* vout);
+
 /* ---- routines: crates/routines ---- */
 
 /* Swizzle::merge_op, routines/src/lib.rs:82-120, bool.rs:49-87:

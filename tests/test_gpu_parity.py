@@ -369,3 +369,76 @@ def test_more_than_2_32_rows(device):
     assert np.array_equal(out, x[keep])
     tail = ag.Int8ArrayGPU(ag.ArrowGpuBuffer(device, a.data.ptr + (1 << 32), 77, owned=False), device, 77, None)
     assert np.array_equal(tail.cast(ag.Int32ArrayGPU).raw_values(), x[1 << 32:].astype(np.int32))
+
+
+# ---- general fused chains: bit-identical to the same ops applied one by one ---------------------
+CHAINS = [
+    [("mul", "B"), ("add", "C"), ("gt", "D")],
+    [("mul", 2.5), ("add", "B"), ("sqrt",), ("lt", 30.0)],
+    [("abs",), ("sqrt",), ("mul", "B"), ("sub", 1.0), ("max", "C")],
+    [("sin",), ("mul", "B"), ("add", "C"), ("cos",), ("gteq", 0.25)],
+    [("div", "B"), ("min", 3.0), ("exp",), ("log2",), ("neg",), ("rem", 0.37), ("add", "C"), ("eq", "D")],
+    [("exp2",)],
+    [("power", 2.0), ("add", 1.0), ("log",), ("sinh",)],
+]
+
+
+def _unfused(a, steps, cols, device):
+    cur = a if isinstance(a, ag.Float32ArrayGPU) else a.cast(ag.Float32ArrayGPU)
+    for step in steps:
+        name = step[0]
+        if len(step) == 1:
+            cur = getattr(cur, name)()
+            continue
+        rhs = cols[step[1]] if isinstance(step[1], str) else step[1]
+        if isinstance(rhs, ag.Float32ArrayGPU):
+            cur = getattr(cur, name)(rhs)
+        elif name in ("add", "sub", "mul", "div", "rem"):
+            cur = getattr(cur, name + "_scalar")(ag.Float32ArrayGPU.from_slice([rhs], device))
+        else:  # min/max/power/compare with a constant: the unfused API needs a broadcast column
+            cur = getattr(cur, name)(ag.Float32ArrayGPU.broadcast(rhs, cur.len, device))
+    return cur
+
+
+@pytest.mark.parametrize("in_dtype", [O.F32, O.I8, O.U8, O.I16, O.U16], ids=lambda d: NAMES[d])
+@pytest.mark.parametrize("chain", range(len(CHAINS)))
+def test_fused_chain_equals_unfused(chain, in_dtype, device):
+    rng = np.random.default_rng(1000 * chain + in_dtype)
+    steps = CHAINS[chain]
+    for n in (0, 1, 5, 33, 4097, 70001):
+        if in_dtype == O.F32:
+            vals = rng.uniform(-8, 8, n).astype(np.float32)
+            if n >= 8:
+                vals[:8] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-40, 7.5, -7.5]
+        else:
+            vals = rand_vals(rng, in_dtype, n)
+        a, _ = make(rng, in_dtype, n, True, device, vals)
+        cols = {}
+        for k, name in enumerate("BCD"):
+            cols[name], _ = make(rng, O.F32, n, k != 1, device, rng.uniform(-4, 4, n).astype(np.float32))
+        fused = K.fused_chain(a, [(s[0], cols[s[1]]) if len(s) > 1 and isinstance(s[1], str) else s for s in steps])
+        want = _unfused(a, steps, cols, device)
+        assert type(fused) is type(want) and fused.len == want.len == n
+        if isinstance(want, ag.BooleanArrayGPU):
+            assert np.array_equal(device.retrive_data(fused.data, O.words(n) * 4), device.retrive_data(want.data, O.words(n) * 4))
+        else:
+            assert same_f32_bits(fused.raw_values(), want.raw_values()), (chain, n)
+        assert np.array_equal(device.retrive_data(fused.null_buffer.bit_buffer, O.words(n) * 4),
+                              device.retrive_data(want.null_buffer.bit_buffer, O.words(n) * 4))
+
+
+def test_fused_chain_vs_oracle_and_limits(device):
+    rng = np.random.default_rng(77)
+    n = 100_003
+    a, oa = make(rng, O.F32, n, True, device, rng.uniform(-10, 10, n).astype(np.float32))
+    b, ob = make(rng, O.F32, n, True, device, rng.uniform(-10, 10, n).astype(np.float32))
+    got = K.fused_chain(a, [("mul", b), ("add", 0.5), ("abs",), ("sqrt",), ("gt", 2.0)])
+    t = oracle_unary("sqrt", oracle_unary("abs", oracle_scalar("add_scalar", oracle_binary("mul", oa, ob), OArr.from_slice(O.F32, [0.5]))))
+    want = O.compare(O.GT, O.F32, t.data, np.full(n, 2.0, np.float32))
+    assert np.array_equal(device.retrive_data(got.data, O.words(n) * 4).view(np.uint32), want)
+    with pytest.raises(ag.Panic):
+        K.fused_chain(a, [("gt", b), ("add", 1.0)])          # a compare must end the chain
+    with pytest.raises(ag.Panic):
+        K.fused_chain(ag.Int32ArrayGPU.from_slice([1], device), [("sqrt",)])
+    with pytest.raises(ag.Panic):
+        K.fused_chain(a, [("neg",)] * 9)
