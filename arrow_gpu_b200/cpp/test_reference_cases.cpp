@@ -146,8 +146,8 @@ int main() {
     CHECK(fused_mul_add_gt(ga, gb, gc, gd).raw_values() == ga.mul(gb).add(gc).gt(gd).raw_values());
     auto chained = fused_chain(ga, {ChainStep::binary(AGPU_MUL, gb), ChainStep::binary(AGPU_ADD, gc), ChainStep::compare(AGPU_GT, gd)});
     CHECK(std::get<BooleanArrayGPU>(chained).raw_values() == ga.mul(gb).add(gc).gt(gd).raw_values());
-    auto vals = fused_chain(Int8ArrayGPU::from_slice({0, 1, 4, 9, -16}, device), {ChainStep::unary(AGPU_ABS), ChainStep::unary(AGPU_SQRT), ChainStep::binary(AGPU_MUL, 2.0f)});
-    CHECK(feq(std::get<Float32ArrayGPU>(vals).raw_values(), {0, 2, 4, 6, 8}));
+    auto chain_vals = fused_chain(Int8ArrayGPU::from_slice({0, 1, 4, 9, -16}, device), {ChainStep::unary(AGPU_ABS), ChainStep::unary(AGPU_SQRT), ChainStep::binary(AGPU_MUL, 2.0f)});
+    CHECK(feq(std::get<Float32ArrayGPU>(chain_vals).raw_values(), {0, 2, 4, 6, 8}));
     auto vals = Int32ArrayGPU::from_optional_slice({10, None, 30, 40, 50, 60}, device);
     auto keep = BooleanArrayGPU::from_optional_slice({true, true, false, None, true, false}, device);
     std::vector<Opt<int32_t>> want = {10, None, 50};
