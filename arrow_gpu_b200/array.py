@@ -12,6 +12,7 @@ stream scope whose `finish()` has nothing left to submit.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import enum
 from typing import Optional, Sequence
@@ -52,6 +53,20 @@ class ArrowType(enum.Enum):
     Date32Type = _ffi.DATE32
 
 
+# At interpreter exit the CUDA runtime(s) of the process are being torn down in an order we do
+# not control (ours is linked statically, torch brings its own): objects that are still alive
+# then must not call back into the library.  The OS reclaims device memory with the process.
+_SHUTDOWN = False
+
+
+def _mark_shutdown() -> None:
+    global _SHUTDOWN
+    _SHUTDOWN = True
+
+
+atexit.register(_mark_shutdown)
+
+
 def _round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
@@ -72,13 +87,13 @@ class GpuDevice:
     def new(cls) -> "GpuDevice":
         return cls(0)
 
-    def __del__(self):
-        try:
-            if getattr(self, "handle", None):
-                lib().agpu_device_destroy(self.handle)
-                self.handle = None
-        except Exception:
-            pass
+    def destroy(self) -> None:
+        """Release the stream.  Never implicit: buffers, events and (when torch interop is used)
+        torch-side objects may still refer to the stream when the Python handle is collected, so a
+        device handle lives until the process ends unless the owner ends it explicitly."""
+        if getattr(self, "handle", None) and not _SHUTDOWN:
+            lib().agpu_device_destroy(self.handle)
+        self.handle = None
 
     # --- buffers
     def create_empty_buffer(self, size: int) -> "ArrowGpuBuffer":
@@ -196,7 +211,7 @@ class GpuEvent:
 
     def __del__(self):
         try:
-            if self.handle:
+            if self.handle and not _SHUTDOWN:
                 lib().agpu_event_destroy(self.handle)
         except Exception:
             pass
@@ -220,7 +235,7 @@ class ArrowGpuBuffer:
 
     def __del__(self):
         try:
-            if self._owned and self.ptr and self.device.handle:
+            if self._owned and self.ptr and self.device.handle and not _SHUTDOWN:
                 if self._kind == "ipc":
                     lib().agpu_ipc_free(self.device.handle, self.ptr)
                 elif self._kind == "peer":

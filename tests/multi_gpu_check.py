@@ -71,6 +71,8 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU check ok: world={world}, {total} of {n} rows kept")
+    del a, o, m, out, taken
+    dev.sync()
     dist.destroy_process_group()
 
 
