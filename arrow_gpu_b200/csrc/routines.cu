@@ -477,21 +477,43 @@ __global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restri
   const bool vec_out = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
   const uint32_t lead = vec_out ? (uint32_t)(off % G) : 0u;  // shift so that 16-byte vectors line up
 
+  if (full) {
+    // branch-free: every row's slot is computed, the store is predicated on its selection bit
+    // (no divergent branches / reconvergence barriers in the hot loop)
 #pragma unroll
-  for (int j = 0; j < GPT; ++j) {
-    const int r = (j * BLOCK + threadIdx.x) * G;  // first row of the granule within the tile
-    const uint32_t sw = sel[r >> 5];
-    const uint32_t bits = (sw >> (r & 31)) & ((1u << G) - 1u);
-    if (bits == 0) continue;
-    uint32_t pos = lead + pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
-    uint32_t vw = 0;
-    if (HAS_V) vw = vsrc[(row0 + r) >> 5] >> (r & 31);
+    for (int j = 0; j < GPT; ++j) {
+      const int r = (j * BLOCK + threadIdx.x) * G;  // first row of the granule within the tile
+      const uint32_t sw = sel[r >> 5];
+      const uint32_t bits = sw >> (r & 31);
+      uint32_t pos = lead + pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
+      uint32_t vw = 0;
+      if (HAS_V) vw = vsrc[(row0 + r) >> 5] >> (r & 31);
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-      if ((bits >> k) & 1u) {
-        stage[pos] = full ? v[j].e[k] : src[row0 + r + k];
-        if (HAS_V && ((vw >> k) & 1u)) atomicOr(&vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
-        ++pos;
+      for (int k = 0; k < G; ++k) {
+        const bool take = (bits >> k) & 1u;
+        if (take) stage[pos] = v[j].e[k];
+        if (HAS_V) {
+          if (take && ((vw >> k) & 1u)) atomicOr(&vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
+        }
+        pos += take ? 1u : 0u;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < GPT; ++j) {
+      const int r = (j * BLOCK + threadIdx.x) * G;
+      const uint32_t sw = sel[r >> 5];
+      const uint32_t bits = (sw >> (r & 31)) & ((1u << G) - 1u);
+      if (bits == 0) continue;
+      uint32_t pos = lead + pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
+      uint32_t vw = 0;
+      if (HAS_V) vw = vsrc[(row0 + r) >> 5] >> (r & 31);
+      for (int k = 0; k < G; ++k) {
+        if ((bits >> k) & 1u) {
+          stage[pos] = src[row0 + r + k];
+          if (HAS_V && ((vw >> k) & 1u)) atomicOr(&vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
+          ++pos;
+        }
       }
     }
   }
