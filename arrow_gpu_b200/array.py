@@ -253,10 +253,16 @@ class ArrowComputePipeline:
     queues, so every `*_op` enqueues its kernel immediately on the device's stream and
     `finish()` only marks the end of the scope (it never waits, like the reference)."""
 
-    def __init__(self, device: GpuDevice, label: Optional[str] = None, profile: bool = False):
+    def __init__(self, device: GpuDevice, label: Optional[str] = None, profile: bool = False, fuse: bool = False):
         self.device = device
         self.label = label
         self.finished = False
+        # fuse=True: f32 op chains recorded on this pipeline (cast -> unary/binary/scalar ops ->
+        # optional compare) are not launched one by one; each maximal linear chain becomes ONE
+        # agpu_fused_chain kernel at finish() (or earlier, when a result is read).  Same results
+        # bit for bit as fuse=False (kernels.py, "auto-fusion").
+        self.fuse = fuse
+        self._lazies: list = []
         # the reference's `profile` cargo feature wraps every compute pass in timestamp queries
         # (gpu_utils/compute_query.rs:3-90); here: a CUDA event pair per recorded op
         self.profile = profile
@@ -274,6 +280,13 @@ class ArrowComputePipeline:
         return self.device.clone_buffer(buffer)
 
     def finish(self) -> None:
+        """compute_pipeline.rs:259-273.  With fuse=True this launches one fused kernel per recorded
+        chain whose result is still referenced and was not absorbed into a longer chain."""
+        for ref in self._lazies:
+            arr = ref()
+            if arr is not None and arr._lazy is not None and not arr._lazy.consumed:
+                arr._materialize()
+        self._lazies = []
         self.finished = True
 
 
@@ -430,7 +443,35 @@ class PrimitiveArrayGpu:
 
     def __init__(self, data: ArrowGpuBuffer, gpu_device: GpuDevice, length: int,
                  null_buffer: Optional[NullBitBufferGpu] = None):
-        self.data, self.gpu_device, self.len, self.null_buffer = data, gpu_device, length, null_buffer
+        self._lazy = None
+        self._data, self.gpu_device, self.len, self._null_buffer = data, gpu_device, length, null_buffer
+
+    # `data` and `null_buffer` are the reference's public fields.  On a fusing pipeline an array may
+    # be a recorded-but-not-yet-launched chain (`_lazy`); touching either field launches it.
+    @property
+    def data(self) -> ArrowGpuBuffer:
+        if self._lazy is not None:
+            self._materialize()
+        return self._data
+
+    @data.setter
+    def data(self, value) -> None:
+        self._data = value
+
+    @property
+    def null_buffer(self) -> Optional[NullBitBufferGpu]:
+        if self._lazy is not None:
+            self._materialize()
+        return self._null_buffer
+
+    @null_buffer.setter
+    def null_buffer(self, value) -> None:
+        self._null_buffer = value
+
+    def _materialize(self) -> None:
+        lazy, self._lazy = self._lazy, None
+        out = lazy.evaluate()
+        self._data, self._null_buffer = out._data, out._null_buffer
 
     # --- constructors
     @classmethod

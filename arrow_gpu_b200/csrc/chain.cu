@@ -22,6 +22,7 @@ struct ChainProgram {
   int op[AGPU_CHAIN_MAX_STEPS];
   int col[AGPU_CHAIN_MAX_STEPS];  // operand column slot for *_COLUMN steps
   float scalar[AGPU_CHAIN_MAX_STEPS];
+  const float* dscalar[AGPU_CHAIN_MAX_STEPS];  // one-element device arrays for *_DEVSCALAR steps
   const float* cols[kMaxCols];
 };
 
@@ -124,6 +125,10 @@ struct ChainOp {
         if (kind == AGPU_STEP_BINARY_SCALAR || kind == AGPU_STEP_COMPARE_SCALAR) {
 #pragma unroll
           for (int k = 0; k < 4 * U; ++k) rhs[k] = p.scalar[s];
+        } else if (kind == AGPU_STEP_BINARY_DEVSCALAR || kind == AGPU_STEP_COMPARE_DEVSCALAR) {
+          const float v = __ldg(p.dscalar[s]);
+#pragma unroll
+          for (int k = 0; k < 4 * U; ++k) rhs[k] = v;
         } else {
           const int c = p.col[s];
 #pragma unroll
@@ -132,7 +137,8 @@ struct ChainOp {
             for (int k = 0; k < 4; ++k)
               rhs[j * 4 + k] = c == 0 ? in4[j].c[0].e[k] : (c == 1 ? in4[j].c[1].e[k] : in4[j].c[2].e[k]);
         }
-        if (kind == AGPU_STEP_BINARY_COLUMN || kind == AGPU_STEP_BINARY_SCALAR) apply_binary<4 * U>(p.op[s], acc, rhs);
+        if (kind == AGPU_STEP_BINARY_COLUMN || kind == AGPU_STEP_BINARY_SCALAR || kind == AGPU_STEP_BINARY_DEVSCALAR)
+          apply_binary<4 * U>(p.op[s], acc, rhs);
         else cmp_op = p.op[s];  // compare is the last step (checked on the host)
       }
     }
@@ -233,6 +239,7 @@ extern "C" int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, 
     p.kind[s] = st.kind;
     p.op[s] = st.op;
     p.scalar[s] = st.scalar;
+    p.dscalar[s] = nullptr;
     p.col[s] = 0;
     switch (st.kind) {
       case AGPU_STEP_UNARY:
@@ -240,15 +247,21 @@ extern "C" int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, 
         break;
       case AGPU_STEP_BINARY_COLUMN:
       case AGPU_STEP_BINARY_SCALAR:
+      case AGPU_STEP_BINARY_DEVSCALAR:
         if (st.op < AGPU_ADD || st.op > AGPU_POW || (st.op >= AGPU_AND && st.op <= AGPU_XOR)) return AGPU_EUNSUPPORTED;
         break;
       case AGPU_STEP_COMPARE_COLUMN:
       case AGPU_STEP_COMPARE_SCALAR:
+      case AGPU_STEP_COMPARE_DEVSCALAR:
         if (st.op < AGPU_GT || st.op > AGPU_EQ) return AGPU_EUNSUPPORTED;
         if (s != n_steps - 1) return AGPU_EINVAL;  // a predicate ends the chain
         is_pred = true;
         break;
       default: return AGPU_EINVAL;
+    }
+    if (st.kind == AGPU_STEP_BINARY_DEVSCALAR || st.kind == AGPU_STEP_COMPARE_DEVSCALAR) {
+      if (!st.operand) return AGPU_EINVAL;
+      p.dscalar[s] = st.operand;
     }
     if (st.kind == AGPU_STEP_BINARY_COLUMN || st.kind == AGPU_STEP_COMPARE_COLUMN) {
       if (!st.operand) return AGPU_EINVAL;

@@ -695,6 +695,16 @@ _CHAIN_COMPARE = {"gt": _ffi.GT, "gteq": _ffi.GTEQ, "lt": _ffi.LT, "lteq": _ffi.
 _CHAIN_INPUT = (Float32ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU, Int16ArrayGPU, UInt16ArrayGPU)
 
 
+class DeviceScalar:
+    """a ONE-element Float32ArrayGPU used as the scalar operand of a chain step (the reference
+    passes scalars this way); read on the device, never copied back to the host"""
+
+    def __init__(self, array):
+        if not isinstance(array, Float32ArrayGPU) or array.len != 1:
+            raise Panic("DeviceScalar needs a one-element Float32ArrayGPU")
+        self.array = array
+
+
 def fused_chain_op(data, steps, pipeline):
     """Evaluate a linear chain in ONE kernel.  `steps` is a list of
          ("sqrt",)                 unary f32 op on the running value
@@ -716,15 +726,18 @@ def fused_chain_op(data, steps, pipeline):
             arr[k].kind, arr[k].op = _ffi.STEP_UNARY, _CHAIN_UNARY[name]
             continue
         if name in _CHAIN_BINARY:
-            op, kinds = _CHAIN_BINARY[name], (_ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_SCALAR)
+            op, kinds = _CHAIN_BINARY[name], (_ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_SCALAR, _ffi.STEP_BINARY_DEVSCALAR)
         elif name in _CHAIN_COMPARE:
             if k != len(steps) - 1:
                 raise Panic("a compare can only end a fused chain")
-            op, kinds, is_pred = _CHAIN_COMPARE[name], (_ffi.STEP_COMPARE_COLUMN, _ffi.STEP_COMPARE_SCALAR), True
+            op, kinds, is_pred = (_CHAIN_COMPARE[name],
+                                  (_ffi.STEP_COMPARE_COLUMN, _ffi.STEP_COMPARE_SCALAR, _ffi.STEP_COMPARE_DEVSCALAR), True)
         else:
             raise Panic(f"fused_chain: unknown step {step!r}")
         arr[k].op = op
-        if isinstance(operand, Float32ArrayGPU):
+        if isinstance(operand, DeviceScalar):
+            arr[k].kind, arr[k].operand = kinds[2], operand.array.data.ptr
+        elif isinstance(operand, Float32ArrayGPU):
             _check_same_len(data, operand, "fused_chain")
             arr[k].kind, arr[k].operand, arr[k].validity = kinds[0], operand.data.ptr, _vptr(operand.null_buffer)
             validities.append(operand.null_buffer)
@@ -745,6 +758,106 @@ def fused_chain(data, steps):
     out = fused_chain_op(data, steps, pipeline)
     pipeline.finish()
     return out
+
+
+# ==========================================================================================
+# auto-fusion: ArrowComputePipeline(device, fuse=True)
+# ==========================================================================================
+# The reference's recorded-chain pattern (crates/arrow/examples/simple.rs:45-72) issues one dispatch
+# per `*_op`.  On a fusing pipeline eligible ops only RECORD: the returned Float32ArrayGPU carries
+# (source column, steps) instead of a buffer.  Applying another eligible op to it extends the chain;
+# a compare ends it and launches the single fused kernel at once; `finish()` launches every chain
+# that was not absorbed into a longer one; reading `data` / `null_buffer` / values of a recorded
+# array launches its own chain on demand.  Anything not eligible falls back to the plain kernel
+# (its lazy operands are launched first), so results never differ from fuse=False.
+import weakref  # noqa: E402
+
+_FUSE_UNARY = set(_CHAIN_UNARY)
+_FUSE_BINARY = {"add", "sub", "mul", "div", "min", "max", "power"}
+_FUSE_SCALAR = {"add_scalar": "add", "sub_scalar": "sub", "mul_scalar": "mul", "div_scalar": "div", "rem_scalar": "rem"}
+_FUSE_COMPARE = set(_CHAIN_COMPARE)
+_MAX_CHAIN_COLS = 3
+
+
+class _LazyChain:
+    def __init__(self, source, steps, pipeline):
+        self.source, self.steps, self.pipeline, self.consumed = source, steps, pipeline, False
+
+    def n_cols(self):
+        return sum(1 for st in self.steps if len(st) > 1 and isinstance(st[1], Float32ArrayGPU))
+
+    def evaluate(self):
+        if not self.steps:      # a bare int -> f32 cast that nothing was chained onto
+            return _cast_to(self.source, Float32ArrayGPU, self.pipeline)
+        return fused_chain_op(self.source, self.steps, self.pipeline)
+
+
+def _lazy_array(source, steps, pipeline):
+    arr = Float32ArrayGPU(None, source.gpu_device, source.len, None)
+    arr._lazy = _LazyChain(source, steps, pipeline)
+    pipeline._lazies.append(weakref.ref(arr))
+    return arr
+
+
+def _extend(self, step, pipeline):
+    """new recorded array = chain of `self` + step (or a fresh chain starting at `self`)"""
+    lazy = self._lazy
+    adds_col = len(step) > 1 and isinstance(step[1], Float32ArrayGPU)
+    if (lazy is not None and lazy.pipeline is pipeline and len(lazy.steps) < _ffi.CHAIN_MAX_STEPS
+            and (not adds_col or lazy.n_cols() < _MAX_CHAIN_COLS)):
+        lazy.consumed = True
+        return lazy.source, lazy.steps + [step]
+    return self, [step]      # `self` (concrete, or launched on demand) becomes the source
+
+
+def _try_fuse(name, self, args):
+    """returns the recorded/fused result, or None when the op is not eligible"""
+    pipeline = args[-1] if args and isinstance(args[-1], ArrowComputePipeline) else None
+    if pipeline is None or not pipeline.fuse or not isinstance(self, PrimitiveArrayGpu):
+        return None
+    base = name[:-3]
+    is_f32 = isinstance(self, Float32ArrayGPU)
+    operand = args[0] if len(args) > 1 else None
+    if base == "cast" and isinstance(self, _TRIG_INT) and self._lazy is None:
+        into = ARRAY_TYPES[operand] if isinstance(operand, ArrowType) else operand
+        if into is Float32ArrayGPU:
+            return _lazy_array(self, [], pipeline)
+        return None
+    if base in _FUSE_UNARY and operand is None:
+        if is_f32 or (base in ("sin", "cos", "sinh") and isinstance(self, _TRIG_INT)):
+            return _lazy_array(*_extend(self, (base,), pipeline), pipeline)
+        return None
+    if not is_f32 or not isinstance(operand, Float32ArrayGPU):
+        return None
+    if base in _FUSE_SCALAR:
+        if operand.len != 1:
+            return None
+        return _lazy_array(*_extend(self, (_FUSE_SCALAR[base], DeviceScalar(operand)), pipeline), pipeline)
+    if operand.len != self.len:
+        return None
+    if base in _FUSE_BINARY:
+        return _lazy_array(*_extend(self, (base, operand), pipeline), pipeline)
+    if base in _FUSE_COMPARE:
+        source, steps = _extend(self, (base, operand), pipeline)
+        return fused_chain_op(source, steps, pipeline)       # a predicate ends the chain: launch now
+    return None
+
+
+def _fusing(name, fn):
+    def wrapper(self, *args, **kwargs):
+        if not kwargs:
+            out = _try_fuse(name, self, args)
+            if out is not None:
+                return out
+        return fn(self, *args, **kwargs)
+    wrapper.__name__ = getattr(fn, "__name__", name)
+    wrapper.__doc__ = fn.__doc__
+    return wrapper
+
+
+for _name, _fn in list(vars(PrimitiveArrayGpu).items()):
+    if _name.endswith("_op") and callable(_fn) and not isinstance(_fn, (classmethod, staticmethod)):
+        setattr(PrimitiveArrayGpu, _name, _fusing(_name, _fn))
 
 
 # ==========================================================================================

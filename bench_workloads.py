@@ -127,6 +127,12 @@ def run(args, rank, world, local_rank, helpers):
             r = K.gt_op_dyn(K.add_op_dyn(K.mul_op_dyn(cols[0], cols[1], p), cols[2], p), cols[3], p)
             p.finish()
             return r
+        def chain_fused():
+            p = ag.ArrowComputePipeline(dev, "chain", fuse=True)
+            r = K.gt_op_dyn(K.add_op_dyn(K.mul_op_dyn(cols[0], cols[1], p), cols[2], p), cols[3], p)
+            p.finish()
+            return r
+
         def chain2():
             p = ag.ArrowComputePipeline(dev, "chain2")
             r = K.add_op_dyn(K.mul_op_dyn(K.sin_op_dyn(cols[0], p), cols[1], p), cols[2], p)
@@ -136,6 +142,7 @@ def run(args, rank, world, local_rank, helpers):
                ("generic fused_chain [mul b, add c, gt d] + 4 bitmaps", 16.75, n,
                 lambda: K.fused_chain(cols[0], [("mul", cols[1]), ("add", cols[2]), ("gt", cols[3])])),
                ("unfused chain mul,add,gt (reference style, 3 kernels)", 33.25, n, chain),
+               ("same recorded chain on ArrowComputePipeline(fuse=True) (auto-fused, 1 kernel)", 16.75, n, chain_fused),
                ("generic fused_chain [sin, mul b, add c] -> f32 + 3 bitmaps", 16.5, n,
                 lambda: K.fused_chain(cols[0], [("sin",), ("mul", cols[1]), ("add", cols[2])])),
                ("unfused sin,mul,add (3 kernels)", 32.875, n, chain2)]

@@ -225,7 +225,11 @@ typedef enum {
   AGPU_STEP_BINARY_COLUMN = 1,
   AGPU_STEP_BINARY_SCALAR = 2,
   AGPU_STEP_COMPARE_COLUMN = 3,
-  AGPU_STEP_COMPARE_SCALAR = 4
+  AGPU_STEP_COMPARE_SCALAR = 4,
+  /* rhs = a ONE-element f32 array on the device (how the reference passes scalars:
+   * arithmetic/src/lib.rs:11-50); `operand` points at it, no host round trip */
+  AGPU_STEP_BINARY_DEVSCALAR = 5,
+  AGPU_STEP_COMPARE_DEVSCALAR = 6
 } agpu_step_kind;
 typedef struct {
   int32_t kind;             /* agpu_step_kind */

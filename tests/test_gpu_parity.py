@@ -442,3 +442,80 @@ def test_fused_chain_vs_oracle_and_limits(device):
         K.fused_chain(ag.Int32ArrayGPU.from_slice([1], device), [("sqrt",)])
     with pytest.raises(ag.Panic):
         K.fused_chain(a, [("neg",)] * 9)
+
+
+# ---- auto-fusing pipeline: same bits as the unfused pipeline, fewer launches ---------------------
+def _record(pipeline, a, b, c, d, s, i8):
+    """a recorded program in the reference's `*_op_dyn` style (crates/arrow/examples/simple.rs:45-72)"""
+    r1 = K.mul_op_dyn(a, b, pipeline)
+    r2 = K.add_op_dyn(r1, c, pipeline)
+    m1 = K.gt_op_dyn(r2, d, pipeline)                         # chain 1: mul, add, gt
+    t1 = K.sqrt_op_dyn(K.abs_op_dyn(K.mul_scalar_op_dyn(a, s, pipeline), pipeline), pipeline)
+    t2 = K.sub_op_dyn(t1, b, pipeline)                        # chain 2: mul_scalar, abs, sqrt, sub  (kept as f32)
+    u1 = K.sin_op_dyn(i8, pipeline)                           # chain 3 starts at an int8 column (fused cast)
+    u2 = K.max_op_dyn(K.add_scalar_op_dyn(u1, s, pipeline), c, pipeline)
+    w = K.add_op_dyn(t2, u2, pipeline)                        # both operands are recorded chains
+    m2 = K.lteq_op_dyn(K.exp_op_dyn(w, pipeline), d, pipeline)
+    both = K.bitwise_and_op_dyn(m1, m2, pipeline)             # not fusable: plain kernel on two bitmaps
+    return {"r2": r2, "m1": m1, "t2": t2, "u2": u2, "w": w, "m2": m2, "both": both}
+
+
+def test_auto_fusing_pipeline(device):
+    rng = np.random.default_rng(99)
+    for n in (0, 7, 4097, 250_001):
+        cols = [make(rng, O.F32, n, k % 2 == 0, device, rng.uniform(-5, 5, n).astype(np.float32))[0] for k in range(4)]
+        s = ag.Float32ArrayGPU.from_slice([1.75], device)
+        i8 = make(rng, O.I8, n, True, device)[0]
+        plain = ag.ArrowComputePipeline(device, "plain")
+        want = _record(plain, *cols, s, i8)
+        plain.finish()
+        l0 = device.launch_count()
+        fusing = ag.ArrowComputePipeline(device, "fused", fuse=True)
+        got = _record(fusing, *cols, s, i8)
+        fusing.finish()
+        fused_launches = device.launch_count() - l0
+        for key in want:
+            g, w = got[key], want[key]
+            assert type(g) is type(w) and g.len == w.len == n, key
+            if isinstance(w, ag.BooleanArrayGPU):
+                assert np.array_equal(device.retrive_data(g.data, O.words(n) * 4), device.retrive_data(w.data, O.words(n) * 4)), (key, n)
+            else:
+                assert same_f32_bits(g.raw_values(), w.raw_values()), (key, n)
+            gv = None if g.null_buffer is None else device.retrive_data(g.null_buffer.bit_buffer, O.words(n) * 4)
+            wv = None if w.null_buffer is None else device.retrive_data(w.null_buffer.bit_buffer, O.words(n) * 4)
+            assert (gv is None) == (wv is None) and (gv is None or np.array_equal(gv, wv)), (key, n)
+        if n:
+            # 15 ops recorded; fused: chains end at m1, t2, u2, w, m2 (+ r2 read back on demand) + the bitmap AND
+            assert fused_launches <= 8, fused_launches
+
+
+def test_auto_fusion_launch_counts(device):
+    n = 1 << 20
+    rng = np.random.default_rng(5)
+    a, b, c, d = (ag.Float32ArrayGPU.from_numpy(rng.uniform(-3, 3, n).astype(np.float32), None, device) for _ in range(4))
+    l0 = device.launch_count()
+    p = ag.ArrowComputePipeline(device, fuse=True)
+    m = K.gt_op_dyn(K.add_op_dyn(K.mul_op_dyn(a, b, p), c, p), d, p)
+    p.finish()
+    assert device.launch_count() - l0 == 1                 # mul, add, gt -> one kernel
+    assert np.array_equal(m.raw_values(), (a.raw_values() * b.raw_values() + c.raw_values()) > d.raw_values())
+    # a result nobody keeps is never computed; a kept intermediate is computed on demand
+    l0 = device.launch_count()
+    p = ag.ArrowComputePipeline(device, fuse=True)
+    r1 = K.mul_op_dyn(a, b, p)
+    r2 = K.sqrt_op_dyn(K.abs_op_dyn(r1, p), p)
+    del r2
+    p.finish()
+    assert device.launch_count() - l0 == 0
+    assert np.array_equal(r1.raw_values(), a.raw_values() * b.raw_values())
+    assert device.launch_count() - l0 == 1
+    # more than 8 steps / 3 operand columns split into several kernels, still identical
+    p = ag.ArrowComputePipeline(device, fuse=True)
+    x = a
+    for k in range(11):
+        x = K.add_op_dyn(K.mul_scalar_op_dyn(x, ag.Float32ArrayGPU.from_slice([0.5], device), p), (b, c, d)[k % 3], p)
+    p.finish()
+    ref = a.raw_values()
+    for k in range(11):
+        ref = ref * np.float32(0.5) + (b, c, d)[k % 3].raw_values()
+    assert same_f32_bits(x.raw_values(), ref)
