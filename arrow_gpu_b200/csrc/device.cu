@@ -197,7 +197,14 @@ extern "C" int agpu_ipc_alloc(agpu_device* dev, size_t bytes, void** out) {
   if (!dev) return AGPU_ENODEVICE;
   AGPU_REQUIRE(out);
   AGPU_CUDA(cudaSetDevice(dev->ordinal));
-  AGPU_CUDA(cudaMalloc(out, bytes ? bytes : 16));
+  // Sizes are rounded up to 32 MiB (2 MiB below that).  Measured on B200 (profiles/
+  // r01_peer_take_probe.md): a 1 999 998 976-byte shard (not a multiple of 2 MiB) mapped into a
+  // peer makes random peer gathers over more than 1 GiB of it 40x slower (0.17 vs 7 G rows/s),
+  // while 1984 MiB and 2048 MiB shards do not — the odd tail is evidently mapped with small
+  // pages and overflows the peer translation caches.
+  const size_t gran = bytes >= (32u << 20) ? (32u << 20) : (2u << 20);
+  const size_t rounded = bytes ? (bytes + gran - 1) / gran * gran : gran;
+  AGPU_CUDA(cudaMalloc(out, rounded));
   return 0;
 }
 

@@ -176,6 +176,14 @@ def run(args, rank, world, local_rank, helpers):
         idx_rnd = _wrap(ag, ag.UInt32ArrayGPU, _randint32(torch, n, 45 + seed, tdev, 0, n), n, dev, keep)
         ops.append(("i32.take sorted stride-1", 12.0, n, lambda: a.take(idx_seq)))
         ops.append(("i32.take uniform random", 12.0, n, lambda: a.take(idx_rnd)))
+        if world > 1:
+            # global row numbers over all shards: the gather kernel reads peer shards over NVLink
+            col = sharded.ShardedColumn(ag.Int32ArrayGPU, a, None, total_rows, dev)
+            keep.append(col)
+            m_g = min(n, 1 << 28)
+            gidx = _wrap(ag, ag.UInt32ArrayGPU, _randint32(torch, m_g, 46 + seed, tdev, 0, min(total_rows, 2**31 - 1)), m_g, dev, keep)
+            ops.append((f"i32.take GLOBAL uniform random over {world} shards (NVLink peer loads, {m_g} rows/GPU)", 12.0, m_g,
+                        lambda: col.take_global(gidx)))
     else:
         raise SystemExit(f"unknown workload {name}")
 
