@@ -219,6 +219,8 @@ int run_chain(agpu_device* dev, const ChainProgram& p, const void* in, void* out
   ChainOp<TI> op{p, (const TI*)in, (float*)out};
   bool al = aligned16(in) && aligned16(out);
   for (int k = 0; k < p.n_cols; ++k) al = al && aligned16(p.cols[k]);
+  // two granules per thread evaluated jointly: 64 registers, 0.80-0.93 of peak; four (126
+  // registers) measured 30 % slower
   if (is_pred) return launch_bits<ChainOp<TI>, 2>(dev, op, (uint32_t*)out, n, bm, al);
   return launch_ew<ChainOp<TI>, 2>(dev, op, n, bm, al);
 }
