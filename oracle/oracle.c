@@ -167,14 +167,24 @@ static inline uint32_t pack4xU8(const uint32_t v[4]) {
  * packed-word scratch: the reference keeps sub-word columns in buffers padded to 4 bytes
  * (primitive_array_gpu.rs:27-31); new buffers are zero-filled (wgpu).
  * ---------------------------------------------------------------------------------------- */
+/* Whole-word, 4-byte aligned buffers are used in place (no copy); only a ragged tail needs the
+ * zero-padded scratch copy.  WFREE / WOUT_DONE know which case they are in. */
+static int word_exact(const void* p, size_t bytes) { return bytes && bytes % 4 == 0 && ((uintptr_t)p & 3u) == 0; }
 static uint32_t* words_from(const void* src, size_t bytes, size_t* nwords) {
   size_t nw = (bytes + 3) / 4;
+  *nwords = nw;
+  if (word_exact(src, bytes)) return (uint32_t*)src;
   uint32_t* w = (uint32_t*)calloc(nw ? nw : 1, 4);
   if (w && bytes) memcpy(w, src, bytes);
-  *nwords = nw;
   return w;
 }
 static uint32_t* words_zero(size_t nwords) { return (uint32_t*)calloc(nwords ? nwords : 1, 4); }
+static uint32_t* words_out(void* dst, size_t bytes, size_t nwords) {
+  if (word_exact(dst, bytes) && nwords * 4 == bytes) return (uint32_t*)dst;
+  return words_zero(nwords);
+}
+#define WFREE(ptr, src) do { if ((const void*)(ptr) != (const void*)(src)) free(ptr); } while (0)
+#define WOUT_DONE(ptr, dst, bytes) do { if ((void*)(ptr) != (void*)(dst)) { memcpy((dst), (ptr), (bytes)); free(ptr); } } while (0)
 
 static inline size_t dtype_size(int dtype) {
   switch (dtype) {
@@ -335,7 +345,7 @@ int oracle_binary(int op, int dtype, const void* a, const void* b, void* out, si
       if (op == AGPU_MIN || op == AGPU_MAX || op == AGPU_AND || op == AGPU_OR || op == AGPU_XOR) {
         /* word level: compare/compute_shaders/u16/min_max.wgsl:13-27, logical u32/logical.wgsl */
         size_t nw; uint32_t* x = words_from(a, n * 2, &nw); uint32_t* y = words_from(b, n * 2, &nw);
-        uint32_t* o = words_zero(nw);
+        uint32_t* o = words_out(out, n * 2, nw);
         OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) {
           if (op == AGPU_MIN || op == AGPU_MAX) {
             uint32_t ll = u16_get_left_half(x[i]), lr = u16_get_left_half(y[i]);
@@ -347,8 +357,8 @@ int oracle_binary(int op, int dtype, const void* a, const void* b, void* out, si
             o[i] = op == AGPU_AND ? (x[i] & y[i]) : op == AGPU_OR ? (x[i] | y[i]) : (x[i] ^ y[i]);
           }
         }
-        memcpy(out, o, n * 2);
-        free(x); free(y); free(o);
+        WOUT_DONE(o, out, n * 2);
+        WFREE(x, a); WFREE(y, b);
         break;
       }
       const uint16_t *x = a, *y = b; uint16_t* o = out;
@@ -360,11 +370,11 @@ int oracle_binary(int op, int dtype, const void* a, const void* b, void* out, si
       if (op == AGPU_POW) return AGPU_EUNSUPPORTED;
       if (op == AGPU_AND || op == AGPU_OR || op == AGPU_XOR) {
         size_t nw; uint32_t* x = words_from(a, n, &nw); uint32_t* y = words_from(b, n, &nw);
-        uint32_t* o = words_zero(nw);
+        uint32_t* o = words_out(out, n, nw);
         OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i)
           o[i] = op == AGPU_AND ? (x[i] & y[i]) : op == AGPU_OR ? (x[i] | y[i]) : (x[i] ^ y[i]);
-        memcpy(out, o, n);
-        free(x); free(y); free(o);
+        WOUT_DONE(o, out, n);
+        WFREE(x, a); WFREE(y, b);
         break;
       }
       const uint8_t *x = a, *y = b; uint8_t* o = out;
@@ -416,7 +426,7 @@ int oracle_scalar(int op, int dtype, const void* a, const void* scalar, void* ou
       if (op == AGPU_ADD) {
         /* word level: arithmetic/compute_shaders/u16/scalar.wgsl:15-23.  The scalar buffer is a
          * one-element u16 array padded to a u32 word. */
-        size_t nw; uint32_t* x = words_from(a, n * 2, &nw); uint32_t* o = words_zero(nw);
+        size_t nw; uint32_t* x = words_from(a, n * 2, &nw); uint32_t* o = words_out(out, n * 2, nw);
         uint32_t operand = s16;
         OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) {
           uint32_t operand_u16 = u16_get_left_half(operand);
@@ -424,8 +434,8 @@ int oracle_scalar(int op, int dtype, const void* a, const void* scalar, void* ou
           uint32_t right = u16_get_right_half(x[i]) + operand_u16;
           o[i] = (left & 0xffffu) + (right << 16);
         }
-        memcpy(out, o, n * 2);
-        free(x); free(o);
+        WOUT_DONE(o, out, n * 2);
+        WFREE(x, a);
         break;
       }
       const uint16_t* x = a; uint16_t* o = out;
@@ -491,10 +501,10 @@ int oracle_unary(int op, int dtype, const void* a, void* out, size_t n) {
   if (op == AGPU_NOT) {
     size_t es = dtype_size(dtype);
     if (!es || dtype == AGPU_F32 || dtype == AGPU_DATE32) return AGPU_EUNSUPPORTED;
-    size_t nw; uint32_t* x = words_from(a, n * es, &nw); uint32_t* o = words_zero(nw);
+    size_t nw; uint32_t* x = words_from(a, n * es, &nw); uint32_t* o = words_out(out, n * es, nw);
     OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) o[i] = ~x[i];
-    memcpy(out, o, n * es);
-    free(x); free(o);
+    WOUT_DONE(o, out, n * es);
+    WFREE(x, a);
     return 0;
   }
   switch (dtype) {
@@ -515,7 +525,7 @@ int oracle_unary(int op, int dtype, const void* a, void* out, size_t n) {
       if (op != AGPU_SIN && op != AGPU_COS && op != AGPU_SINH) return AGPU_EUNSUPPORTED;
       /* {i8,u8}/trigonometry.wgsl:11-33: unpack4x{I,U}8 -> f32() -> fn -> 4 x f32 */
       size_t nw; uint32_t* x = words_from(a, n, &nw);
-      float* o = (float*)calloc(nw * 4 + 1, 4);
+      float* o = (n % 4 == 0) ? (float*)out : (float*)calloc(nw * 4 + 1, 4);
       OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) {
         int k = 1;
         if (dtype == AGPU_I8) {
@@ -526,15 +536,15 @@ int oracle_unary(int op, int dtype, const void* a, void* out, size_t n) {
           for (int j = 0; j < 4; ++j) o[i * 4 + j] = f32_unop(op, (float)u[j], &k);
         }
       }
-      memcpy(out, o, n * 4);
-      free(x); free(o);
+      WOUT_DONE(o, out, n * 4);
+      WFREE(x, a);
       return 0;
     }
     case AGPU_I16: case AGPU_U16: {
       if (op != AGPU_SIN && op != AGPU_COS && op != AGPU_SINH) return AGPU_EUNSUPPORTED;
       /* {i16,u16}/trigonometry.wgsl: get_left_half/get_right_half -> f32() -> fn */
       size_t nw; uint32_t* x = words_from(a, n * 2, &nw);
-      float* o = (float*)calloc(nw * 2 + 1, 4);
+      float* o = (n % 2 == 0) ? (float*)out : (float*)calloc(nw * 2 + 1, 4);
       OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) {
         int k = 1;
         if (dtype == AGPU_I16) {
@@ -545,8 +555,8 @@ int oracle_unary(int op, int dtype, const void* a, void* out, size_t n) {
           o[i * 2 + 1] = f32_unop(op, (float)u16_get_right_half(x[i]), &k);
         }
       }
-      memcpy(out, o, n * 4);
-      free(x); free(o);
+      WOUT_DONE(o, out, n * 4);
+      WFREE(x, a);
       return 0;
     }
     default: return AGPU_EUNSUPPORTED;
@@ -619,7 +629,7 @@ int oracle_compare(int op, int dtype, const void* a, const void* b, uint32_t* ou
     }
     out_bits[w] = bits;
   }
-  free(x); free(y);
+  WFREE(x, a); WFREE(y, b);
   return 0;
 }
 
@@ -661,10 +671,14 @@ int oracle_shift(int op, int dtype, const void* a, const uint32_t* counts, void*
   if (es != 1 && es != 2) return AGPU_EUNSUPPORTED;
   size_t per = 4 / es;
   size_t nw; uint32_t* x = words_from(a, n * es, &nw);
-  size_t ncw; uint32_t* c = words_from(counts, n * 4, &ncw);
-  uint32_t* cp = (uint32_t*)calloc(nw * per + 1, 4); /* counts padded to whole words of lanes */
-  memcpy(cp, c, n * 4);
-  uint32_t* o = words_zero(nw);
+  const uint32_t* cp = counts; /* counts padded to whole words of lanes only when the tail is ragged */
+  uint32_t* cpad = NULL;
+  if (nw * per != n) {
+    cpad = (uint32_t*)calloc(nw * per + 1, 4);
+    memcpy(cpad, counts, n * 4);
+    cp = cpad;
+  }
+  uint32_t* o = words_out(out, n * es, nw);
   OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) {
     const uint32_t* r = cp + (size_t)i * per;
     if (dtype == AGPU_I8) {
@@ -688,8 +702,8 @@ int oracle_shift(int op, int dtype, const void* a, const uint32_t* counts, void*
       o[i] = (lo & 0x0000ffffu) | ((hi << 16) & 0xffff0000u);
     }
   }
-  memcpy(out, o, n * es);
-  free(x); free(c); free(cp); free(o);
+  WOUT_DONE(o, out, n * es);
+  WFREE(x, a); free(cpad);
   return 0;
 }
 
@@ -734,9 +748,10 @@ int oracle_cast(int src, int dst, const void* a, void* out, size_t n) {
   if (src == AGPU_F32) {
     if (dst != AGPU_U8) return AGPU_EUNSUPPORTED;
     size_t nw = (n + 3) / 4;
-    float* x = (float*)calloc(nw * 4 + 1, 4);
-    memcpy(x, a, n * 4);
-    uint32_t* o = words_zero(nw);
+    const float* x = a;
+    float* xpad = NULL;
+    if (n % 4) { xpad = (float*)calloc(nw * 4 + 1, 4); memcpy(xpad, a, n * 4); x = xpad; }
+    uint32_t* o = words_out(out, n, nw);
     OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) {
       size_t idx = 4 * (size_t)i;
       uint32_t w = 0;
@@ -746,8 +761,8 @@ int oracle_cast(int src, int dst, const void* a, void* out, size_t n) {
       w |= (f32_to_u32(x[idx + 3]) % 256u) << 24;
       o[i] = w;
     }
-    memcpy(out, o, n);
-    free(x); free(o);
+    WOUT_DONE(o, out, n);
+    free(xpad);
     return 0;
   }
   size_t ss = dtype_size(src), ds = dtype_size(dst);
@@ -766,7 +781,7 @@ int oracle_cast(int src, int dst, const void* a, void* out, size_t n) {
   size_t nw; uint32_t* x = words_from(a, n * ss, &nw);
   size_t per = 4 / ss;
   size_t out_words = nw * per * ds / 4;
-  uint32_t* o = words_zero(out_words);
+  uint32_t* o = words_out(out, n * ds, out_words);
   OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) {
     int32_t lanes[4];
     if (ss == 1) {
@@ -787,8 +802,8 @@ int oracle_cast(int src, int dst, const void* a, void* out, size_t n) {
       o[np + 1] = ((uint32_t)lanes[2] & 0x0000ffffu) | ((uint32_t)lanes[3] << 16);
     }
   }
-  memcpy(out, o, n * ds);
-  free(x); free(o);
+  WOUT_DONE(o, out, n * ds);
+  WFREE(x, a);
   return 0;
 }
 
@@ -809,9 +824,10 @@ int oracle_merge(int dtype, const void* a, const void* b, const uint32_t* mask, 
   size_t nw; uint32_t* x = words_from(a, n * es, &nw); uint32_t* y = words_from(b, n * es, &nw);
   size_t per = 4 / es;
   size_t mw = bit_words(nw * per);
-  uint32_t* m = words_zero(mw + 1);
-  memcpy(m, mask, bit_words(n) * 4);
-  uint32_t* o = words_zero(nw);
+  const uint32_t* m = mask;
+  uint32_t* mpad = NULL;
+  if (nw * per != n) { mpad = words_zero(mw + 1); memcpy(mpad, mask, bit_words(n) * 4); m = mpad; }
+  uint32_t* o = words_out(out, n * es, nw);
   OMP_FOR for (idx_t i = 0; i < (idx_t)nw; ++i) {
     if (es == 4) { /* 32bit/merge.wgsl:22-30 */
       o[i] = get_bit(m, (size_t)i) ? x[i] : y[i];
@@ -829,8 +845,8 @@ int oracle_merge(int dtype, const void* a, const void* b, const uint32_t* mask, 
       o[i] = w;
     }
   }
-  memcpy(out, o, n * es);
-  free(x); free(y); free(m); free(o);
+  WOUT_DONE(o, out, n * es);
+  WFREE(x, a); WFREE(y, b); free(mpad);
   return 0;
 }
 
