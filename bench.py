@@ -310,6 +310,7 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": len(ops) * rows * e2e_steps * world / (e2e_ms * 1e-3), "unit": "rows/s", "steps": e2e_steps,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms / e2e_steps, 3)}
 
+    run_ours.host_columns = pinned     # reused by the cpu_baseline leg (same synthetic columns)
     result = {
         "metric": "rows/s (row-operations per second over the 55 ops of config 2; achieved HBM GB/s per op in per_op)",
         "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -347,10 +348,13 @@ def cpu_runner():
     return O, run
 
 
-def time_cpu(sample_rows: int, steps: int, warmup: int):
+def time_cpu(sample_rows: int, steps: int, warmup: int, cols=None):
     O, run = cpu_runner()
     ops = cfg2_ops()
-    cols = cfg2_columns(sample_rows)
+    if cols is None:
+        cols = cfg2_columns(sample_rows)
+    else:
+        cols = {k: v[:sample_rows] for k, v in cols.items()}
     outs = {t: np.empty(sample_rows, dtype=NPT[t]) for t in NPT}
     for _ in range(warmup):
         for spec in ops:
@@ -396,7 +400,9 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="rows (default: the workload's own size; cfg2: 256 Mi per GPU)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="BASELINE.json configs[k-1]; cfg2 is the bench line, the others are scaling/parity configs")
-    ap.add_argument("--cpu-rows", type=int, default=1 << 24, help="rows of the bounded CPU sample")
+    ap.add_argument("--cpu-rows", type=int, default=ROWS_CFG2,
+                    help="rows of the CPU sample (default: the full 256 Mi-row columns — a step is 1-4 s of CPU work on "
+                         "16-24 host threads, and a sample that fits the host's last-level cache would flatter the CPU)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -441,7 +447,7 @@ def main():
         res = run_ours(args, rank, world, local_rank)
         if rank == 0:
             if not args.no_cpu_baseline and world == 1:
-                res["cpu_baseline"] = time_cpu(args.cpu_rows, 3, 1)
+                res["cpu_baseline"] = time_cpu(min(args.cpu_rows, args.rows), 3, 1, cols=run_ours.host_columns)
             else:
                 res["cpu_baseline"] = None
             emit(res)
