@@ -35,6 +35,7 @@ SIGNATURES = {
     "agpu_error_string": (C.c_char_p, [_i]),
     "agpu_alloc": (_i, [_p, _sz, C.POINTER(_p)]),
     "agpu_free": (_i, [_p, _p]),
+    "agpu_trim": (_i, [_p]),
     "agpu_h2d": (_i, [_p, _p, _p, _sz]),
     "agpu_d2h": (_i, [_p, _p, _p, _sz]),
     "agpu_d2h_async": (_i, [_p, _p, _p, _sz]),

@@ -4,6 +4,10 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/agpu.h"
 
 struct agpu_device {
@@ -12,6 +16,15 @@ struct agpu_device {
   cudaMemPool_t pool;
   unsigned long long launches;  // kernels launched through this handle
   int sm_count;
+  // Stream-ordered caching allocator in front of cudaMallocAsync: every op allocates a fresh
+  // output (like the reference), so freed blocks are kept by size and handed out again without
+  // going back to the driver pool — whose remapping when block sizes alternate costs
+  // milliseconds (measured: profiles/r01_size_sweep.md).  Safe because all work of a handle is
+  // ordered on its one stream: a block freed after op k can only be reused by op k+1 or later.
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;       // size -> block
+  std::unordered_map<void*, size_t> block_size;   // every block handed out or cached
+  size_t cached_bytes = 0;
 };
 
 struct agpu_event {

@@ -8,6 +8,8 @@
 
 extern "C" int agpu_abi_version(void) { return AGPU_ABI_VERSION; }
 
+static void release_cache(agpu_device* dev);
+
 extern "C" int agpu_device_count(int* out) {
   if (!out) return AGPU_EINVAL;
   int n = 0;
@@ -56,6 +58,10 @@ extern "C" int agpu_device_create(int ordinal, agpu_device** out) {
 extern "C" int agpu_device_destroy(agpu_device* dev) {
   if (!dev) return AGPU_EINVAL;
   cudaSetDevice(dev->ordinal);
+  {
+    std::lock_guard<std::mutex> lock(dev->mu);
+    release_cache(dev);
+  }
   cudaStreamSynchronize(dev->stream);
   cudaStreamDestroy(dev->stream);
   delete dev;
@@ -78,20 +84,67 @@ extern "C" const char* agpu_error_string(int code) {
   return "unknown agpu error";
 }
 
+static size_t round_block(size_t bytes) {
+  if (bytes == 0) bytes = 16;  // keep a distinct non-NULL pointer for empty columns
+  const size_t gran = bytes < (1u << 20) ? 512 : (bytes < (64u << 20) ? (1u << 20) : (16u << 20));
+  return (bytes + gran - 1) / gran * gran;
+}
+
+static void release_cache(agpu_device* dev) {  // caller holds dev->mu
+  for (auto& kv : dev->free_blocks) {
+    cudaFreeAsync(kv.second, dev->stream);
+    dev->block_size.erase(kv.second);
+  }
+  dev->free_blocks.clear();
+  dev->cached_bytes = 0;
+}
+
 extern "C" int agpu_alloc(agpu_device* dev, size_t bytes, void** out) {
   if (!dev) return AGPU_ENODEVICE;
   if (!out) return AGPU_EINVAL;
   *out = nullptr;
-  if (bytes == 0) bytes = 16;  // keep a distinct non-NULL pointer for empty columns
+  const size_t want = round_block(bytes);
+  std::lock_guard<std::mutex> lock(dev->mu);
+  // best fit among cached blocks, but never waste more than 25 % (+1 MiB) of a block
+  auto it = dev->free_blocks.lower_bound(want);
+  if (it != dev->free_blocks.end() && it->first <= want + want / 4 + (1u << 20)) {
+    *out = it->second;
+    dev->cached_bytes -= it->first;
+    dev->free_blocks.erase(it);
+    return 0;
+  }
   AGPU_CUDA(cudaSetDevice(dev->ordinal));
-  AGPU_CUDA(cudaMallocAsync(out, bytes, dev->stream));
+  cudaError_t e = cudaMallocAsync(out, want, dev->stream);
+  if (e == cudaErrorMemoryAllocation) {  // give the cache back to the driver and retry once
+    cudaGetLastError();
+    release_cache(dev);
+    cudaStreamSynchronize(dev->stream);
+    e = cudaMallocAsync(out, want, dev->stream);
+  }
+  if (e != cudaSuccess) return (int)e;
+  dev->block_size[*out] = want;
   return 0;
 }
 
 extern "C" int agpu_free(agpu_device* dev, void* ptr) {
   if (!dev) return AGPU_ENODEVICE;
   if (!ptr) return 0;
-  AGPU_CUDA(cudaFreeAsync(ptr, dev->stream));
+  std::lock_guard<std::mutex> lock(dev->mu);
+  auto it = dev->block_size.find(ptr);
+  if (it == dev->block_size.end()) {  // not one of ours (should not happen): plain stream-ordered free
+    AGPU_CUDA(cudaFreeAsync(ptr, dev->stream));
+    return 0;
+  }
+  dev->free_blocks.emplace(it->second, ptr);
+  dev->cached_bytes += it->second;
+  return 0;
+}
+
+/* give every cached block back to the driver pool (e.g. before another library needs the memory) */
+extern "C" int agpu_trim(agpu_device* dev) {
+  if (!dev) return AGPU_ENODEVICE;
+  std::lock_guard<std::mutex> lock(dev->mu);
+  release_cache(dev);
   return 0;
 }
 

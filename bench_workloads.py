@@ -13,7 +13,7 @@ import statistics
 
 import numpy as np
 
-ROWS = {"cfg1": 1_048_576, "cfg3": 1_000_000_000, "cfg4": 4_000_000_000, "cfg5": 4_000_000_000}
+ROWS = {"cfg1": 1_048_576, "cfg3": 1_000_000_000, "cfg4": 4_000_000_000, "cfg5": 4_000_000_000, "sweep": 1 << 30}
 
 
 def _wrap(ag, cls, tensor, n, dev, keep):
@@ -184,6 +184,31 @@ def run(args, rank, world, local_rank, helpers):
             gidx = _wrap(ag, ag.UInt32ArrayGPU, _randint32(torch, m_g, 46 + seed, tdev, 0, min(total_rows, 2**31 - 1)), m_g, dev, keep)
             ops.append((f"i32.take GLOBAL uniform random over {world} shards (NVLink peer loads, {m_g} rows/GPU)", 12.0, m_g,
                         lambda: col.take_global(gidx)))
+    elif name == "sweep":
+        # column-size sweep of one binary op with validity (f32 add, 12.375 B/row) from the
+        # reference's test sizes up to 1 Gi rows: where launch latency ends and HBM begins.
+        # 20 calls back to back per measurement (no host sync in between).
+        base_a = _uniform(torch, n, -1000, 1000, 1 + seed, tdev)
+        base_b = _uniform(torch, n, -1000, 1000, 2 + seed, tdev)
+        va = _bitmap(torch, n, 0.9, 3 + seed, tdev)
+        vb = _bitmap(torch, n, 0.9, 4 + seed, tdev)
+        keep.extend([base_a, base_b, va, vb])
+        for rows in (1 << 16, 1 << 18, 1 << 20, 1 << 22, 1 << 24, 1 << 26, 1 << 28, 1 << 30):
+            if rows > n:
+                break
+            def arr(t, bits, rows=rows):
+                x = ag.Float32ArrayGPU(ag.ArrowGpuBuffer(dev, t.data_ptr(), rows * 4, owned=False), dev, rows, None)
+                x.null_buffer = ag.NullBitBufferGpu(ag.ArrowGpuBuffer(dev, bits.data_ptr(), (rows + 31) // 32 * 4, owned=False), rows, dev)
+                return x
+            xa, xb = arr(base_a, va), arr(base_b, vb)
+            reps = 20
+
+            def many(xa=xa, xb=xb):
+                out = None
+                for _ in range(reps):
+                    out = xa.add(xb)
+                return out
+            ops.append((f"f32.add+validity rows=2^{rows.bit_length() - 1} (x{reps} back to back)", 12.375, rows * reps, many))
     else:
         raise SystemExit(f"unknown workload {name}")
 

@@ -117,10 +117,15 @@ uint64_t agpu_launch_count(agpu_device* dev);
 const char* agpu_error_string(int code);
 int agpu_abi_version(void);
 
-/* create_empty_buffer, gpu_device.rs:183-192 — stream-ordered, NOT zero-filled */
+/* create_empty_buffer, gpu_device.rs:183-192 — stream-ordered, NOT zero-filled.  A pointer may
+ * only be used by work ordered after the allocation on this handle's stream (or on another
+ * stream that waits for it), and must be freed through the same handle. */
 int agpu_alloc(agpu_device* dev, size_t bytes, void** out);
-/* Drop of wgpu::Buffer — stream-ordered free, safe right after enqueueing work */
+/* Drop of wgpu::Buffer — stream-ordered free, safe right after enqueueing work.  Freed blocks
+ * are cached per handle and reused by later agpu_alloc calls of a similar size. */
 int agpu_free(agpu_device* dev, void* ptr);
+/* return every cached free block to the driver */
+int agpu_trim(agpu_device* dev);
 /* create_gpu_buffer_with_data, gpu_device.rs:171-181 (host may be pageable or pinned) */
 int agpu_h2d(agpu_device* dev, void* dst_dev, const void* src_host, size_t bytes);
 /* retrive_data, gpu_device.rs:232-265 — copies and waits for the stream */
@@ -193,7 +198,9 @@ int agpu_bitmap_not(agpu_device* dev, const uint32_t* a, uint32_t* out, size_t n
 
 /* ---- casts: cast/src/lib.rs:40-87,135-161 (matrix), boolean_cast.rs, f32_cast.rs ----
  * src/dst dtype pairs outside the reference matrix return AGPU_EUNSUPPORTED.
- * For src == AGPU_BOOL `a` is a bitmap.  Same-width casts and bitcast are copies. */
+ * For src == AGPU_BOOL `a` is a bitmap.  Same-width casts are copies, and so is the one
+ * bitcast the reference has, BitCast<Float32ArrayGPU> for UInt32ArrayGPU (cast/src/lib.rs:90-108,
+ * 187-192), requested here as (AGPU_U32 -> AGPU_F32): the bits are reinterpreted, not converted. */
 int agpu_cast(agpu_device* dev, int src_dtype, int dst_dtype, const void* a, void* out,
               size_t n, const uint32_t* va, uint32_t* vout);
 
