@@ -1,14 +1,29 @@
 // compare.cu — agpu_compare (compare/src/lib.rs:85-111,142-162) and the fused f32 expression
 // ((a*b)+c) > d of BASELINE.json config 3.
+#include <type_traits>
+
 #include "bits.cuh"
 
 namespace {
 
-struct PGt { template <typename T> __device__ __forceinline__ bool operator()(T a, T b) const { return a > b; } };
-struct PGe { template <typename T> __device__ __forceinline__ bool operator()(T a, T b) const { return a >= b; } };
-struct PLt { template <typename T> __device__ __forceinline__ bool operator()(T a, T b) const { return a < b; } };
-struct PLe { template <typename T> __device__ __forceinline__ bool operator()(T a, T b) const { return a <= b; } };
-struct PEq { template <typename T> __device__ __forceinline__ bool operator()(T a, T b) const { return a == b; } };
+// Each predicate also knows how to compare a packed word of 8- or 16-bit lanes at once (SIMD-in-
+// word video intrinsics): the result has 0xFF / 0xFFFF in every lane where the predicate holds.
+#define AGPU_PRED(NAME, EXPR, S4, U4, S2, U2)                                                        \
+  struct NAME {                                                                                      \
+    template <typename T> __device__ __forceinline__ bool operator()(T a, T b) const { return EXPR; } \
+    template <typename T> static __device__ __forceinline__ uint32_t lanes(uint32_t a, uint32_t b) {  \
+      if constexpr (std::is_same<T, int8_t>::value) return S4(a, b);                                 \
+      else if constexpr (std::is_same<T, uint8_t>::value) return U4(a, b);                           \
+      else if constexpr (std::is_same<T, int16_t>::value) return S2(a, b);                           \
+      else return U2(a, b);                                                                          \
+    }                                                                                                \
+  };
+AGPU_PRED(PGt, a > b, __vcmpgts4, __vcmpgtu4, __vcmpgts2, __vcmpgtu2)
+AGPU_PRED(PGe, a >= b, __vcmpges4, __vcmpgeu4, __vcmpges2, __vcmpgeu2)
+AGPU_PRED(PLt, a < b, __vcmplts4, __vcmpltu4, __vcmplts2, __vcmpltu2)
+AGPU_PRED(PLe, a <= b, __vcmples4, __vcmpleu4, __vcmples2, __vcmpleu2)
+AGPU_PRED(PEq, a == b, __vcmpeq4, __vcmpeq4, __vcmpeq2, __vcmpeq2)
+#undef AGPU_PRED
 
 // f32 compares are IEEE (any NaN -> false, -0 == +0); integers compare with their own
 // signedness — native sub-word lanes instead of the reference's get_*_byte/get_*_half helpers.
@@ -21,8 +36,22 @@ struct CmpOp {
   __device__ __forceinline__ In load(size_t g) const { return In{ld_vec<T, G>(a, g), ld_vec<T, G>(b, g)}; }
   __device__ __forceinline__ uint32_t bits(size_t, const In& in) const {
     uint32_t m = 0;
+    if constexpr (sizeof(T) < 4) {
+      // one lane mask per packed word, then the mask's lane bits are gathered with a multiply:
+      // bytes: (m & 0x08040201) * 0x01010101 >> 24 = 4 bits; halves: (m & 0x00020001) * 0x00010001 >> 16 = 2 bits
+      uint32_t wa[4], wb[4];
+      memcpy(wa, &in.a, 16);
+      memcpy(wb, &in.b, 16);
 #pragma unroll
-    for (int k = 0; k < G; ++k) m |= (uint32_t)P{}(in.a.e[k], in.b.e[k]) << k;
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t lanes = P::template lanes<T>(wa[k], wb[k]);
+        if constexpr (sizeof(T) == 1) m |= (((lanes & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+        else m |= ((((lanes & 0x00020001u) * 0x00010001u) >> 16) & 3u) << (2 * k);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < G; ++k) m |= (uint32_t)P{}(in.a.e[k], in.b.e[k]) << k;
+    }
     return m;
   }
   __device__ __forceinline__ bool bit_at(size_t i) const { return P{}(a[i], b[i]); }

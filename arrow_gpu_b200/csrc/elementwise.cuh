@@ -108,6 +108,11 @@ struct UnaryOp {
   __device__ __forceinline__ void tail(size_t i) const { out[i] = f(a[i]); }
 };
 
+// functors that can process a packed 32-bit word of sub-word lanes at once expose
+// `static constexpr bool kWord = true` and `static uint32_t word(uint32_t, uint32_t)`
+template <class F, class = void> struct HasWordOp : std::false_type {};
+template <class F> struct HasWordOp<F, std::void_t<decltype(F::kWord)>> : std::bool_constant<F::kWord> {};
+
 template <typename TA, typename TB, typename TO, class F>
 struct BinaryOp {
   static constexpr int G = 16 / MaxOf<MaxOf<sizeof(TA), sizeof(TB)>::v, sizeof(TO)>::v;
@@ -119,8 +124,17 @@ struct BinaryOp {
   __device__ __forceinline__ In load(size_t g) const { return In{ld_vec<TA, G>(a, g), ld_vec<TB, G>(b, g)}; }
   __device__ __forceinline__ void run(size_t g, const In& in) const {
     Vec<TO, G> o;
+    if constexpr (HasWordOp<F>::value && std::is_same<TA, TB>::value && std::is_same<TA, TO>::value && sizeof(TA) * G == 16) {
+      uint32_t wa[4], wb[4], wo[4];
+      memcpy(wa, &in.a, 16);
+      memcpy(wb, &in.b, 16);
 #pragma unroll
-    for (int k = 0; k < G; ++k) o.e[k] = f(in.a.e[k], in.b.e[k]);
+      for (int k = 0; k < 4; ++k) wo[k] = F::word(wa[k], wb[k]);
+      memcpy(&o, wo, 16);
+    } else {
+#pragma unroll
+      for (int k = 0; k < G; ++k) o.e[k] = f(in.a.e[k], in.b.e[k]);
+    }
     st_vec<TO, G>(out, g, o);
   }
   __device__ __forceinline__ void tail(size_t i) const { out[i] = f(a[i], b[i]); }

@@ -62,16 +62,32 @@ template <typename T> struct OpRem {
   }
 };
 // ---- min/max: compare/compute_shaders/*/min_max.wgsl (f32: NaN-ignoring, -0 < +0; u32 unsigned: Q3) ----
+// 8/16-bit lanes: whole 32-bit words through the SIMD-in-word video intrinsics (4 or 2 lanes per
+// instruction sequence) instead of extract / compare / insert per lane.
 template <typename T> struct OpMin {
   __device__ __forceinline__ T operator()(T a, T b) const {
     if constexpr (std::is_same<T, float>::value) return fminf(a, b);
     else return a < b ? a : b;
+  }
+  static constexpr bool kWord = sizeof(T) < 4;
+  static __device__ __forceinline__ uint32_t word(uint32_t a, uint32_t b) {
+    if constexpr (std::is_same<T, int8_t>::value) return __vmins4(a, b);
+    else if constexpr (std::is_same<T, uint8_t>::value) return __vminu4(a, b);
+    else if constexpr (std::is_same<T, int16_t>::value) return __vmins2(a, b);
+    else return __vminu2(a, b);
   }
 };
 template <typename T> struct OpMax {
   __device__ __forceinline__ T operator()(T a, T b) const {
     if constexpr (std::is_same<T, float>::value) return fmaxf(a, b);
     else return a > b ? a : b;
+  }
+  static constexpr bool kWord = sizeof(T) < 4;
+  static __device__ __forceinline__ uint32_t word(uint32_t a, uint32_t b) {
+    if constexpr (std::is_same<T, int8_t>::value) return __vmaxs4(a, b);
+    else if constexpr (std::is_same<T, uint8_t>::value) return __vmaxu4(a, b);
+    else if constexpr (std::is_same<T, int16_t>::value) return __vmaxs2(a, b);
+    else return __vmaxu2(a, b);
   }
 };
 // ---- logical: logical/compute_shaders/{i32,u32}/logical.wgsl ----
@@ -120,11 +136,18 @@ template <typename T> struct OpNot { __device__ __forceinline__ T operator()(T a
 // f32 math: math/compute_shaders/f32/floatunary.wgsl; trig: trigonometry/compute_shaders/*
 // The input type TI is converted exactly to f32 first (the reference's fused cast+trig shaders).
 template <typename TI> struct FSqrt { __device__ __forceinline__ float operator()(TI a) const { return __fsqrt_rn((float)a); } };
-template <typename TI> struct FCbrt {  // floatunary.wgsl:46-54
+// floatunary.wgsl:46-54: cbrt(x) = sign(x) * pow(|x|, 1.0/3.0) with the f32 constant 1/3 =
+// 0.3333333433.  powf costs ~70 instructions, so the same value is computed as
+//   |x|^(1/3f) = cbrt(|x|) * |x|^d,  d = 1/3f - 1/3 = 9.934e-9,  |x|^d = 1 + d*ln|x| (+ O(1e-12))
+// i.e. cbrtf (1 ULP) plus a sub-ULP correction: half the instructions, and closer to the oracle's
+// pow(x, (double)(1/3f)) than powf's own 4 ULP bound (tests: <= 2 ULP).
+template <typename TI> struct FCbrt {
   __device__ __forceinline__ float operator()(TI a) const {
-    float x = (float)a;
-    const float third = 1.0f / 3.0f;
-    return x < 0.0f ? -powf(-x, third) : powf(x, third);
+    const float x = (float)a;
+    const float m = fabsf(x);
+    float r = cbrtf(m);
+    if (m > 0.0f && m < __int_as_float(0x7f800000)) r = fmaf(r * 9.934107e-9f, logf(m), r);
+    return x < 0.0f ? -r : r;   // NaN -> NaN, -0.0 takes the non-negative branch like the shader
   }
 };
 template <typename TI> struct FExp { __device__ __forceinline__ float operator()(TI a) const { return expf((float)a); } };

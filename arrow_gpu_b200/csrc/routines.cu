@@ -405,8 +405,11 @@ __global__ void __launch_bounds__(1024) filter_scan_kernel(uint64_t* __restrict_
   if (threadIdx.x == 0) *total = carry_s;
 }
 
+// One CTA compacts a "super tile" of M = 4/sizeof(U) count-tiles, i.e. always 16 KiB of rows
+// (4096 x 4-byte, 8192 x 2-byte or 16384 x 1-byte rows): the per-tile barriers and prefix sums are
+// amortised over the same number of bytes for every element width.
 template <typename U, bool HAS_V, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restrict__ src,
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) filter_scatter_kernel(const U* __restrict__ src,
                                                                 const uint32_t* __restrict__ vsrc,
                                                                 const uint32_t* __restrict__ mask,
                                                                 const uint32_t* __restrict__ vmask, const size_t n,
@@ -414,19 +417,24 @@ __global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restri
                                                                 const uint64_t* __restrict__ group_offsets,
                                                                 U* __restrict__ out, uint32_t* vout) {
   constexpr int G = 16 / sizeof(U);                   // rows per 16-byte granule
-  constexpr int GPT = kFilterTileRows / G / BLOCK;    // granules per thread
-  __shared__ __align__(16) U stage[kFilterTileRows + G];
-  __shared__ uint32_t sel[kFilterTileWords];
-  __shared__ uint32_t pre[kFilterTileWords];
-  __shared__ uint32_t vstage[HAS_V ? kFilterTileWords + 1 : 1];
+  constexpr int M = 4 / sizeof(U);                    // count-tiles per super tile
+  constexpr int ROWS = kFilterTileRows * M;           // rows per super tile (16 KiB of rows)
+  constexpr int WORDS = ROWS / 32;                    // selection words per super tile
+  constexpr int WPL = WORDS / 32;                     // selection words per lane of warp 0
+  constexpr int GPT = ROWS / G / BLOCK;               // granules per thread (= 4 for BLOCK 256)
+  __shared__ __align__(16) U stage[ROWS + G];
+  __shared__ uint32_t sel[WORDS];
+  __shared__ uint32_t pre[WORDS];
+  __shared__ uint32_t vstage[HAS_V ? WORDS + 1 : 1];
+  __shared__ uint8_t vbyte[HAS_V ? ROWS + G : 1];     // validity of each compacted row, one byte each
   __shared__ uint64_t off_s;
   __shared__ uint32_t count_s;
 
-  const size_t tile = blockIdx.x;
+  const size_t tile = blockIdx.x;                     // super tile index
   const size_t nwords = (n + 31) / 32;
-  const size_t w0 = tile * kFilterTileWords;
-  const size_t row0 = tile * kFilterTileRows;
-  const bool full = row0 + kFilterTileRows <= n;
+  const size_t w0 = tile * WORDS;
+  const size_t row0 = tile * ROWS;
+  const bool full = row0 + ROWS <= n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // everything that comes from global memory is requested up front: the rows (independent of
@@ -439,26 +447,23 @@ __global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restri
   uint32_t before = 0;
   uint64_t goff = 0;
   if (warp == 1) {  // warp 1: output offset = group offset + counts of the earlier tiles of the group
-    const size_t gstart = tile / kFilterGroupTiles * kFilterGroupTiles;
-    if (gstart + lane < tile) before += counts[gstart + lane];
-    if (gstart + 32 + lane < tile) before += counts[gstart + 32 + lane];
-    if (lane == 0) goff = group_offsets[tile / kFilterGroupTiles];
+    const size_t t0 = tile * M;  // first count-tile of this super tile (M divides the group size)
+    const size_t gstart = t0 / kFilterGroupTiles * kFilterGroupTiles;
+    if (gstart + lane < t0) before += counts[gstart + lane];
+    if (gstart + 32 + lane < t0) before += counts[gstart + 32 + lane];
+    if (lane == 0) goff = group_offsets[t0 / kFilterGroupTiles];
   }
-  for (int w = threadIdx.x; w < kFilterTileWords; w += BLOCK) {
-    sel[w] = sel_word(mask, vmask, w0 + w, nwords, n);
-    if (HAS_V) vstage[w] = 0u;
-  }
-  if (HAS_V && threadIdx.x == 0) vstage[kFilterTileWords] = 0u;
+  for (int w = threadIdx.x; w < WORDS; w += BLOCK) sel[w] = sel_word(mask, vmask, w0 + w, nwords, n);
   if (warp == 1) {
 #pragma unroll
     for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
     if (lane == 0) off_s = goff + before;
   }
   __syncthreads();
-  if (warp == 0) {  // warp 0: exclusive prefix of the 128 popcounts, 4 words per lane
-    uint32_t c[4], s = 0;
+  if (warp == 0) {  // warp 0: exclusive prefix of the popcounts, WPL consecutive words per lane
+    uint32_t c[WPL], s = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { c[k] = __popc(sel[lane * 4 + k]); s += c[k]; }
+    for (int k = 0; k < WPL; ++k) { c[k] = __popc(sel[lane * WPL + k]); s += c[k]; }
     uint32_t incl = s;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restri
     }
     uint32_t e = incl - s;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { pre[lane * 4 + k] = e; e += c[k]; }
+    for (int k = 0; k < WPL; ++k) { pre[lane * WPL + k] = e; e += c[k]; }
     if (lane == 31) count_s = incl;
   }
   __syncthreads();
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restri
         const bool take = (bits >> k) & 1u;
         if (take) stage[pos] = v[j].e[k];
         if (HAS_V) {
-          if (take && ((vw >> k) & 1u)) atomicOr(&vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
+          if (take) vbyte[pos] = (uint8_t)((vw >> k) & 1u);
         }
         pos += take ? 1u : 0u;
       }
@@ -503,7 +508,7 @@ __global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restri
     for (int j = 0; j < GPT; ++j) {
       const int r = (j * BLOCK + threadIdx.x) * G;
       const uint32_t sw = sel[r >> 5];
-      const uint32_t bits = (sw >> (r & 31)) & ((1u << G) - 1u);
+      const uint32_t bits = (sw >> (r & 31)) & ((G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u));
       if (bits == 0) continue;
       uint32_t pos = lead + pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
       uint32_t vw = 0;
@@ -511,7 +516,7 @@ __global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restri
       for (int k = 0; k < G; ++k) {
         if ((bits >> k) & 1u) {
           stage[pos] = src[row0 + r + k];
-          if (HAS_V && ((vw >> k) & 1u)) atomicOr(&vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
+          if (HAS_V) vbyte[pos] = (uint8_t)((vw >> k) & 1u);
           ++pos;
         }
       }
@@ -539,7 +544,14 @@ __global__ void __launch_bounds__(BLOCK) filter_scatter_kernel(const U* __restri
     for (uint32_t i = threadIdx.x; i < count; i += BLOCK) out[off + i] = stage[i];
   }
   if (HAS_V) {
+    // the validity bytes of 32 consecutive compacted rows become one word with a warp ballot
     const uint32_t lw_n = (count + 31) / 32;
+    for (uint32_t w = warp; w < lw_n; w += BLOCK / 32) {
+      const uint32_t i = w * 32 + lane;
+      const uint32_t word = __ballot_sync(0xFFFFFFFFu, i < count && vbyte[lead + i] != 0);
+      if (lane == 0) vstage[w] = word;
+    }
+    __syncthreads();
     const uint32_t s = (uint32_t)(off & 31);
     for (uint32_t w = threadIdx.x; w < lw_n; w += BLOCK) {
       const uint32_t val = vstage[w];
@@ -784,6 +796,7 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
   if (tiles > 0x7FFFFFFFull) return AGPU_EINVAL;
   if (!aligned16(src)) return AGPU_EINVAL;  // tile bases must be 16-byte aligned
   constexpr int BLOCK = 256;  // measured: 128-thread CTAs (more resident tiles) are 2-6 % slower
+  const size_t super_tiles = ceil_div(n, (size_t)kFilterTileRows * (4 / sizeof(U)));
   // The TMA-staged persistent variant is kept for A/B profiling only: with 2 x 16 KiB row buffers
   // + a 16 KiB stage only 4 CTAs fit per SM and it measured 4.9 ms vs 3.4 ms for this kernel's
   // 8 independent CTAs per SM on 4 G rows at 10 % selectivity (profiles/r01_filter_variants.md).
@@ -797,10 +810,10 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
   }
   if (vsrc && vout) {
     AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
-    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true, BLOCK>), (unsigned)tiles, BLOCK, 0, (const U*)src, vsrc, mask,
+    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
                 vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
   } else {
-    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)tiles, BLOCK, 0, (const U*)src, vsrc, mask,
+    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
                 vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
   }
   return agpu_finish_launch();

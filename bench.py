@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=None, help="rows (default: the workload's own size; cfg2: 256 Mi per GPU)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "sweep"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "sweep", "allops"],
                     help="BASELINE.json configs[k-1]; cfg2 is the bench line, the others are scaling/parity configs")
     ap.add_argument("--cpu-rows", type=int, default=ROWS_CFG2,
                     help="rows of the CPU sample (default: the full 256 Mi-row columns — a step is 1-4 s of CPU work on "

@@ -13,7 +13,7 @@ import statistics
 
 import numpy as np
 
-ROWS = {"cfg1": 1_048_576, "cfg3": 1_000_000_000, "cfg4": 4_000_000_000, "cfg5": 4_000_000_000, "sweep": 1 << 30}
+ROWS = {"allops": 268_435_456, "cfg1": 1_048_576, "cfg3": 1_000_000_000, "cfg4": 4_000_000_000, "cfg5": 4_000_000_000, "sweep": 1 << 30}
 
 
 def _wrap(ag, cls, tensor, n, dev, keep):
@@ -184,6 +184,58 @@ def run(args, rank, world, local_rank, helpers):
             gidx = _wrap(ag, ag.UInt32ArrayGPU, _randint32(torch, m_g, 46 + seed, tdev, 0, min(total_rows, 2**31 - 1)), m_g, dev, keep)
             ops.append((f"i32.take GLOBAL uniform random over {world} shards (NVLink peer loads, {m_g} rows/GPU)", 12.0, m_g,
                         lambda: col.take_global(gidx)))
+    elif name == "allops":
+        # every remaining (op, dtype) family of the path at 256 Mi rows, to find kernels that fall
+        # short of the roofline (config 2 already covers sub-word arithmetic/logical/shift/cast)
+        f = [_wrap(ag, ag.Float32ArrayGPU, _uniform(torch, n, 0.5, 50.0, 60 + k + seed, tdev), n, dev, keep) for k in range(2)]
+        f[0] = nullable(f[0], 0.9, 70 + seed)
+        unit = _wrap(ag, ag.Float32ArrayGPU, _uniform(torch, n, -1.0, 1.0, 63 + seed, tdev), n, dev, keep)
+        i32 = [_wrap(ag, ag.Int32ArrayGPU, _randint32(torch, n, 64 + k + seed, tdev), n, dev, keep) for k in range(2)]
+        u32 = [_wrap(ag, ag.UInt32ArrayGPU, _randint32(torch, n, 66 + k + seed, tdev), n, dev, keep) for k in range(2)]
+        small = _wrap(ag, ag.Int32ArrayGPU, _randint32(torch, n, 68 + seed, tdev, -6, 12), n, dev, keep)
+        cnt = _wrap(ag, ag.UInt32ArrayGPU, _randint32(torch, n, 69 + seed, tdev, 0, 32), n, dev, keep)
+
+        def sub(t, cls):
+            g = torch.Generator(device=tdev)
+            g.manual_seed(80 + seed)
+            info = torch.iinfo(t)
+            x = torch.randint(info.min, info.max + 1, (n,), generator=g, device=tdev, dtype=torch.int32).to(t)
+            return _wrap(ag, cls, x, n, dev, keep)
+        i8a, i8b = sub(torch.int8, ag.Int8ArrayGPU), sub(torch.int8, ag.Int8ArrayGPU)
+        u16a, u16b = sub(torch.int16, ag.UInt16ArrayGPU), sub(torch.int16, ag.UInt16ArrayGPU)
+        mbits = _bitmap(torch, n, 0.5, 90 + seed, tdev)
+        keep.append(mbits)
+        m = ag.BooleanArrayGPU(ag.ArrowGpuBuffer(dev, mbits.data_ptr(), mbits.numel(), owned=False), dev, n, None)
+        m2 = ag.BooleanArrayGPU(ag.ArrowGpuBuffer(dev, mbits.data_ptr(), mbits.numel(), owned=False), dev, n, None)
+        sc_f = ag.Float32ArrayGPU.from_slice([1.5], dev)
+        sc_i = ag.Int32ArrayGPU.from_slice([7], dev)
+        ops = [
+            ("f32.add (+validity)", 12.25, n, lambda: f[0].add(f[1])), ("f32.div", 12.25, n, lambda: f[0].div(f[1])),
+            ("f32.min", 12.25, n, lambda: f[0].min(f[1])), ("f32.power", 12.25, n, lambda: f[0].power(f[1])),
+            ("f32.rem_scalar", 8.25, n, lambda: f[0].rem_scalar(sc_f)), ("f32.neg", 8.25, n, lambda: f[0].neg()),
+            ("f32.abs", 8.25, n, lambda: f[0].abs()), ("f32.cbrt", 8.25, n, lambda: f[0].cbrt()),
+            ("f32.exp2", 8.25, n, lambda: f[0].exp2()), ("f32.log", 8.25, n, lambda: f[0].log()),
+            ("f32.log2", 8.25, n, lambda: f[0].log2()), ("f32.acos", 8, n, lambda: unit.acos()),
+            ("f32.sinh", 8, n, lambda: unit.sinh()), ("f32.gt -> bitmap", 8.375, n, lambda: f[0].gt(f[1])),
+            ("f32.eq -> bitmap", 8.375, n, lambda: f[0].eq(f[1])), ("f32.sum", 4, n, lambda: f[1].sum()),
+            ("f32.cast u8", 5.25, n, lambda: f[0].cast(ag.UInt8ArrayGPU)),
+            ("i32.add", 12, n, lambda: i32[0].add(i32[1])), ("i32.div_scalar", 8, n, lambda: i32[0].div_scalar(sc_i)),
+            ("i32.rem_scalar", 8, n, lambda: i32[0].rem_scalar(sc_i)), ("i32.max", 12, n, lambda: i32[0].max(i32[1])),
+            ("i32.abs", 8, n, lambda: i32[0].abs()), ("i32.power (|p| small)", 12, n, lambda: i32[0].power(small)),
+            ("i32.lt -> bitmap", 8.125, n, lambda: i32[0].lt(i32[1])), ("i32.shl", 12, n, lambda: i32[0].bitwise_shl(cnt)),
+            ("i32.sum", 4, n, lambda: i32[0].sum()), ("u32.xor", 12, n, lambda: u32[0].bitwise_xor(u32[1])),
+            ("u32.bitcast f32", 8, n, lambda: u32[0].bitcast(ag.Float32ArrayGPU)),
+            ("i8.gt -> bitmap", 2.125, n, lambda: i8a.gt(i8b)), ("i8.min", 3, n, lambda: i8a.min(i8b)),
+            ("i8.sin -> f32 (fused cast)", 5, n, lambda: i8a.sin()), ("i8.merge", 3.125, n, lambda: i8a.merge(i8b, m)),
+            ("u16.lteq -> bitmap", 4.125, n, lambda: u16a.lteq(u16b)), ("u16.max", 6, n, lambda: u16a.max(u16b)),
+            ("u16.cos -> f32 (fused cast)", 6, n, lambda: u16a.cos()), ("u16.merge", 6.125, n, lambda: u16a.merge(u16b, m)),
+            ("f32.merge (+validity of a)", 12.375, n, lambda: f[0].merge(f[1], m)),
+            ("bool.and", 0.375, n, lambda: m.bitwise_and(m2)), ("bool.not", 0.25, n, lambda: m.bitwise_not()),
+            ("bool.all", 0.125, n, lambda: m.all()), ("bool.cast f32", 4.125, n, lambda: m.cast(ag.Float32ArrayGPU)),
+            ("bool.merge", 0.5, n, lambda: m.merge(m2, m)),
+            ("i8.filter s=0.5", 1.125 + 0.5, n, lambda: i8a.filter(m)), ("u16.filter s=0.5", 2.125 + 1, n, lambda: u16a.filter(m)),
+            ("f32.filter s=0.5 (+validity)", 4.25 + 2.0625, n, lambda: f[0].filter(m)),
+        ]
     elif name == "sweep":
         # column-size sweep of one binary op with validity (f32 add, 12.375 B/row) from the
         # reference's test sizes up to 1 Gi rows: where launch latency ends and HBM begins.
