@@ -146,7 +146,8 @@ template <typename TI> struct FCbrt {
     const float x = (float)a;
     const float m = fabsf(x);
     float r = cbrtf(m);
-    if (m > 0.0f && m < __int_as_float(0x7f800000)) r = fmaf(r * 9.934107e-9f, logf(m), r);
+    // the correction is < 1e-6 relative, so ln|x| only needs ~3 digits: the SFU's lg2 is plenty
+    if (m > 0.0f && m < __int_as_float(0x7f800000)) r = fmaf(r * (9.934107e-9f * 0.69314718f), __log2f(m), r);
     return x < 0.0f ? -r : r;   // NaN -> NaN, -0.0 takes the non-negative branch like the shader
   }
 };
