@@ -99,9 +99,11 @@ int run_sum(agpu_device* dev, const T* a, size_t n, T* out_dev) {
   // ping-pong scratch for the partials of each pass
   const size_t cap = ceil_div(n, (size_t)256);
   T* buf[2] = {nullptr, nullptr};
-  if (cap > 1) {
-    AGPU_CUDA(cudaMallocAsync((void**)&buf[0], cap * sizeof(T), dev->stream));
-    AGPU_CUDA(cudaMallocAsync((void**)&buf[1], ceil_div(cap, (size_t)256) * sizeof(T), dev->stream));
+  if (cap > 1) {  // scratch for the partials comes from the handle's block cache
+    int rc0 = agpu_alloc(dev, cap * sizeof(T), (void**)&buf[0]);
+    if (rc0) return rc0;
+    rc0 = agpu_alloc(dev, ceil_div(cap, (size_t)256) * sizeof(T), (void**)&buf[1]);
+    if (rc0) { agpu_free(dev, buf[0]); return rc0; }
   }
   int which = 0, rc = 0;
   while (true) {
@@ -116,8 +118,8 @@ int run_sum(agpu_device* dev, const T* a, size_t n, T* out_dev) {
     len = groups;
     which ^= 1;
   }
-  if (buf[0]) cudaFreeAsync(buf[0], dev->stream);
-  if (buf[1]) cudaFreeAsync(buf[1], dev->stream);
+  if (buf[0]) agpu_free(dev, buf[0]);
+  if (buf[1]) agpu_free(dev, buf[1]);
   return rc;
 }
 
