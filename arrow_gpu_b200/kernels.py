@@ -11,9 +11,6 @@ Nothing here computes on the host; there is no CPU fallback.
 """
 from __future__ import annotations
 
-import ctypes as C
-from typing import Optional
-
 import numpy as np
 
 from . import _ffi

@@ -11,8 +11,6 @@ from __future__ import annotations
 import ctypes as C
 import statistics
 
-import numpy as np
-
 ROWS = {"allops": 268_435_456, "cfg1": 1_048_576, "cfg3": 1_000_000_000, "cfg4": 4_000_000_000, "cfg5": 4_000_000_000, "sweep": 1 << 30}
 
 

@@ -1,6 +1,6 @@
 import sys, os
 sys.path.insert(0, os.getcwd())
-import numpy as np, torch
+import torch
 import arrow_gpu_b200 as ag
 dev = ag.GpuDevice(0)
 n = 4_000_000_000

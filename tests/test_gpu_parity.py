@@ -1,8 +1,6 @@
 """GPU: randomized bit-parity of every (op, dtype) against the oracle on the same seeded inputs,
 at ragged sizes (0, 1, word/tile boundaries +-1, > one tile), with and without nulls and through
 unaligned views; ULP bounds for f32 transcendentals; size-independent properties at large N."""
-import ctypes as C
-
 import numpy as np
 import pytest
 

@@ -8,7 +8,7 @@ import pytest
 import arrow_gpu_b200 as ag
 import oracle as O
 from helpers import OArr, oracle_filter, oracle_merge, oracle_put, oracle_take
-from test_gpu_parity import ALL_CLS, NAMES, SIZES, assert_same, make, rand_vals
+from test_gpu_parity import NAMES, SIZES, assert_same, make
 
 pytestmark = pytest.mark.gpu
 
