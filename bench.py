@@ -270,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
             if c not in order:
                 order.append(c)
 
-    def e2e_step():
+    def e2e_step(read_back=True):
         live, ready = {}, {}
         for name in order:
             c = col_cls.get(name) or cls[name.split(".")[0]]
@@ -287,9 +287,10 @@ def run_ours(args, rank, world, local_rank):
                     dev.wait_event(ready[c])
                     waited.add(c)
             out = run(spec, live, scalars)
-            view = out_stage[: out.len * out.NP.itemsize].view(out.NP)
-            out.raw_values(out=view, wait=False)
-            d2h += view.nbytes
+            if read_back:
+                view = out_stage[: out.len * out.NP.itemsize].view(out.NP)
+                out.raw_values(out=view, wait=False)
+                d2h += view.nbytes
         dev.sync()
         up.sync()
         return h2d, d2h
@@ -308,7 +309,15 @@ def run_ours(args, rank, world, local_rank):
         dev.sync()
         e2e_ms = sharded.max_over_ranks(max(elapsed(ev0, ev1), (time.perf_counter() - t0) * 1e3))
         e2e = {"value": len(ops) * rows * e2e_steps * world / (e2e_ms * 1e-3), "unit": "rows/s", "steps": e2e_steps,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms / e2e_steps, 3)}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms / e2e_steps, 3),
+               "pcie_GBps": {"h2d": round(h2d / (e2e_ms / e2e_steps * 1e-3) / 1e9, 1),
+                             "d2h": round(d2h / (e2e_ms / e2e_steps * 1e-3) / 1e9, 1)}}
+        # where the e2e time goes: the same step with the 55 result columns left on the device
+        # (uploads + compute only) — not the headline, it shows that e2e is the D2H link's time
+        t0 = time.perf_counter()
+        e2e_step(read_back=False)
+        e2e["upload_and_compute_only_ms_per_step"] = round(
+            sharded.max_over_ranks((time.perf_counter() - t0) * 1e3), 3)
 
     run_ours.host_columns = pinned     # reused by the cpu_baseline leg (same synthetic columns)
     result = {
@@ -344,7 +353,7 @@ def cpu_runner():
             return O.unary(O.NOT, dt[t], ins[0], out=out)
         if kind == "shift":
             return O.shift(O.SHL if op == "shl" else O.SHR, dt[t], ins[0], ins[1], out=out)
-        return O.cast(dt[t], dt[d], ins[0])
+        return O.cast(dt[t], dt[d], ins[0], out=out)
     return O, run
 
 
@@ -371,6 +380,37 @@ def time_cpu(sample_rows: int, steps: int, warmup: int, cols=None):
                                       f"(oracle/oracle.c, OpenMP, {O.num_threads()} threads; the reference's own "
                                       "wgpu/lavapipe path cannot be built here)",
             "ms_per_step": round(total / steps * 1e3, 2)}
+
+
+def time_arrow_cpu(cols, sample_rows: int = 1 << 24):
+    """cross-check named by the north star: Arrow's own CPU kernels (pyarrow.compute, the C++ Arrow
+    library; arrow-rs is not in this image) on the ops of config 2 whose semantics they share —
+    wrapping add/sub/mul, and/or/xor/not, widening casts; one thread per call, bounded sample"""
+    try:
+        import pyarrow as pa
+        import pyarrow.compute as pc
+    except ImportError:
+        return None
+    fn = {"add": pc.add, "sub": pc.subtract, "mul": pc.multiply, "and": pc.bit_wise_and, "or": pc.bit_wise_or,
+          "xor": pc.bit_wise_xor, "not": pc.bit_wise_not}
+    pat = {"i8": pa.int8(), "u8": pa.uint8(), "i16": pa.int16(), "u16": pa.uint16(), "i32": pa.int32(),
+           "u32": pa.uint32(), "f32": pa.float32()}
+    arrs = {k: pa.array(v[:sample_rows]) for k, v in cols.items()}
+    todo = [s for s in cfg2_ops() if s[1] in ("binary", "scalar", "unary") or (s[1] == "cast" and s[2] != "f32")]
+    t0 = time.perf_counter()
+    for _label, kind, t, op, d in todo:
+        a = arrs[f"{t}.a"]
+        if kind == "binary":
+            fn[op](a, arrs[f"{t}.b"])
+        elif kind == "scalar":
+            fn[op](a, pa.scalar(3, pat[t]))
+        elif kind == "unary":
+            fn[op](a)
+        else:
+            pc.cast(a, pat[d])
+    dt = time.perf_counter() - t0
+    return {"value": len(todo) * sample_rows / dt, "unit": "rows/s", "cores": 1, "ops": len(todo),
+            "sample": f"pyarrow.compute {pa.__version__}, {len(todo)} of the 55 ops x {sample_rows} rows, one pass"}
 
 
 def run_reference(args, rank):
@@ -448,6 +488,8 @@ def main():
         if rank == 0:
             if not args.no_cpu_baseline and world == 1:
                 res["cpu_baseline"] = time_cpu(min(args.cpu_rows, args.rows), 3, 1, cols=run_ours.host_columns)
+                res["cpu_baseline"]["arrow_cross_check"] = time_arrow_cpu(run_ours.host_columns,
+                                                                          min(1 << 24, args.rows))
             else:
                 res["cpu_baseline"] = None
             emit(res)

@@ -151,14 +151,15 @@ def bitmap_not(a, n_bits):
     return out
 
 
-def cast(src, dst, a, n=None):
+def cast(src, dst, a, n=None, out=None):
     if src == BOOL:
         a = np.ascontiguousarray(a, dtype=np.uint32)
         assert n is not None
     else:
         a = _arr(a, src)
         n = len(a)
-    out = np.empty(n, dtype=NP[dst])
+    if out is None:
+        out = np.empty(n, dtype=NP[dst])
     _chk(lib().oracle_cast(src, dst, _p(a), _p(out), C.c_size_t(n)), "cast")
     return out
 
