@@ -405,11 +405,26 @@ __global__ void __launch_bounds__(1024) filter_scan_kernel(uint64_t* __restrict_
   if (threadIdx.x == 0) *total = carry_s;
 }
 
+// store `val` at shared-memory byte address `sa` and advance `sa` by one element iff bit != 0
+template <typename U>
+__device__ __forceinline__ void stage_if(uint32_t& sa, U val, uint32_t bit) {
+  if constexpr (sizeof(U) == 4) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t@p add.u32 %0, %0, 4;\n\t}"
+                 : "+r"(sa) : "r"((uint32_t)val), "r"(bit) : "memory");
+  } else if constexpr (sizeof(U) == 2) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t@p add.u32 %0, %0, 2;\n\t}"
+                 : "+r"(sa) : "h"((uint16_t)val), "r"(bit) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                 : "+r"(sa) : "r"((uint32_t)val), "r"(bit) : "memory");
+  }
+}
+
 // One CTA compacts a "super tile" of M = 4/sizeof(U) count-tiles, i.e. always 16 KiB of rows
 // (4096 x 4-byte, 8192 x 2-byte or 16384 x 1-byte rows): the per-tile barriers and prefix sums are
 // amortised over the same number of bytes for every element width.
 template <typename U, bool HAS_V, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) filter_scatter_kernel(const U* __restrict__ src,
+__global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1024 : 2048) / BLOCK) filter_scatter_kernel(const U* __restrict__ src,
                                                                 const uint32_t* __restrict__ vsrc,
                                                                 const uint32_t* __restrict__ mask,
                                                                 const uint32_t* __restrict__ vmask, const size_t n,
@@ -482,6 +497,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) filter_scatter_kernel(con
   const bool vec_out = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
   const uint32_t lead = vec_out ? (uint32_t)(off % G) : 0u;  // shift so that 16-byte vectors line up
 
+  const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
+  const uint32_t vbyte_sa = (uint32_t)__cvta_generic_to_shared(vbyte);
   if (full) {
     // branch-free: every row's slot is computed, the store is predicated on its selection bit
     // (no divergent branches / reconvergence barriers in the hot loop)
@@ -493,14 +510,15 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) filter_scatter_kernel(con
       uint32_t pos = lead + pre[r >> 5] + __popc(sw & ((1u << (r & 31)) - 1u));
       uint32_t vw = 0;
       if (HAS_V) vw = vsrc[(row0 + r) >> 5] >> (r & 31);
+      // per row: one predicated store and one predicated address bump (written in PTX: the
+      // compiler's form of `pos += take` is a 3-instruction select-and-add per row)
+      uint32_t sa = stage_sa + pos * (uint32_t)sizeof(U);
+      uint32_t va = vbyte_sa + pos;
 #pragma unroll
       for (int k = 0; k < G; ++k) {
-        const bool take = (bits >> k) & 1u;
-        if (take) stage[pos] = v[j].e[k];
-        if (HAS_V) {
-          if (take) vbyte[pos] = (uint8_t)((vw >> k) & 1u);
-        }
-        pos += take ? 1u : 0u;
+        const uint32_t bit = bits & (1u << k);
+        stage_if<U>(sa, v[j].e[k], bit);
+        if (HAS_V) stage_if<uint8_t>(va, (uint8_t)((vw >> k) & 1u), bit);
       }
     }
   } else {
@@ -808,14 +826,21 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
     }
     return launch_filter_tma<U, false>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout);
   }
+  static const int block_env = getenv("AGPU_FILTER_BLOCK") ? atoi(getenv("AGPU_FILTER_BLOCK")) : 0;
+#define AGPU_FILTER_LAUNCH(HV, B)                                                                                   \
+  AGPU_LAUNCH(dev, (filter_scatter_kernel<U, HV, B>), (unsigned)super_tiles, B, 0, (const U*)src, vsrc, mask, vmask, n, \
+              sc.counts, sc.group_offsets, (U*)out, vout)
   if (vsrc && vout) {
     AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
-    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
-                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
+    if (block_env == 512) { AGPU_FILTER_LAUNCH(true, 512); }
+    else if (block_env == 1024) { AGPU_FILTER_LAUNCH(true, 1024); }
+    else { AGPU_FILTER_LAUNCH(true, BLOCK); }
   } else {
-    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
-                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
+    if (block_env == 512) { AGPU_FILTER_LAUNCH(false, 512); }
+    else if (block_env == 1024) { AGPU_FILTER_LAUNCH(false, 1024); }
+    else { AGPU_FILTER_LAUNCH(false, BLOCK); }
   }
+#undef AGPU_FILTER_LAUNCH
   return agpu_finish_launch();
 }
 
