@@ -79,3 +79,20 @@ def test_product_never_imports_oracle():
     subprocess.run([sys.executable, "-c", code], cwd=ROOT, check=True)
     deps = subprocess.run(["ldd", os.path.join(pkg, "lib", "libagpu.so")], capture_output=True, text=True).stdout
     assert "oracle" not in deps
+
+
+def test_rust_ffi_module_matches_header(ffi):
+    """include/agpu_ffi.rs (the extern "C" module of INTEGRATION.md) is generated from the header:
+    it must be current and declare every function with the argument count ctypes binds"""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(root, "include", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    committed = open(os.path.join(root, "include", "agpu_ffi.rs")).read()
+    assert committed == gen.generate(), "run python include/gen_rust_ffi.py"
+    declared = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (agpu_\w+)\((.*?)\)(?: ->|;)", committed)}
+    assert set(declared) == set(ffi.SIGNATURES)
+    for name, (_ret, args) in ffi.SIGNATURES.items():
+        n_args = len([a for a in declared[name].split(",") if a.strip()])
+        assert n_args == len(args), name
