@@ -89,6 +89,7 @@ STEP_UNARY, STEP_BINARY_COLUMN, STEP_BINARY_SCALAR, STEP_COMPARE_COLUMN, STEP_CO
 STEP_BINARY_DEVSCALAR, STEP_COMPARE_DEVSCALAR = 5, 6
 CHAIN_MAX_STEPS = 8
 SIGNATURES["agpu_fused_chain"] = (_i, [_p, _i, _p, _u32p, C.POINTER(ChainStep), _i, _p, _sz, _u32p])
+SIGNATURES["agpu_fused_chain_int"] = (_i, [_p, _i, _p, _u32p, C.POINTER(ChainStep), _i, _p, _sz, _u32p])
 
 _lib = None
 

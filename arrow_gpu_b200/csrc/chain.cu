@@ -263,13 +263,13 @@ extern "C" int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, 
     }
     if (st.kind == AGPU_STEP_BINARY_DEVSCALAR || st.kind == AGPU_STEP_COMPARE_DEVSCALAR) {
       if (!st.operand) return AGPU_EINVAL;
-      p.dscalar[s] = st.operand;
+      p.dscalar[s] = (const float*)st.operand;
     }
     if (st.kind == AGPU_STEP_BINARY_COLUMN || st.kind == AGPU_STEP_COMPARE_COLUMN) {
       if (!st.operand) return AGPU_EINVAL;
       if (p.n_cols == kMaxCols) return AGPU_EUNSUPPORTED;
       p.col[s] = p.n_cols;
-      p.cols[p.n_cols] = st.operand;
+      p.cols[p.n_cols] = (const float*)st.operand;
       vals[1 + p.n_cols] = st.validity;
       ++p.n_cols;
     }

@@ -693,12 +693,13 @@ _CHAIN_INPUT = (Float32ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU, Int16ArrayGPU, UIn
 
 
 class DeviceScalar:
-    """a ONE-element Float32ArrayGPU used as the scalar operand of a chain step (the reference
-    passes scalars this way); read on the device, never copied back to the host"""
+    """a ONE-element array used as the scalar operand of a chain step (the reference passes
+    scalars this way); read on the device, never copied back to the host.  Float32ArrayGPU for
+    fused_chain, the column's own type for fused_chain_int."""
 
     def __init__(self, array):
-        if not isinstance(array, Float32ArrayGPU) or array.len != 1:
-            raise Panic("DeviceScalar needs a one-element Float32ArrayGPU")
+        if not isinstance(array, PrimitiveArrayGpu) or array.len != 1:
+            raise Panic("DeviceScalar needs a one-element array")
         self.array = array
 
 
@@ -733,6 +734,8 @@ def fused_chain_op(data, steps, pipeline):
             raise Panic(f"fused_chain: unknown step {step!r}")
         arr[k].op = op
         if isinstance(operand, DeviceScalar):
+            if not isinstance(operand.array, Float32ArrayGPU):
+                raise Panic("fused_chain: a device scalar must be a one-element Float32ArrayGPU")
             arr[k].kind, arr[k].operand = kinds[2], operand.array.data.ptr
         elif isinstance(operand, Float32ArrayGPU):
             _check_same_len(data, operand, "fused_chain")
@@ -757,6 +760,76 @@ def fused_chain(data, steps):
     return out
 
 
+_INT_CHAIN_UNARY = {"bitwise_not": _ffi.NOT, "abs": _ffi.ABS}
+_INT_CHAIN_BINARY = {"add": _ffi.ADD, "sub": _ffi.SUB, "mul": _ffi.MUL, "div": _ffi.DIV, "rem": _ffi.REM,
+                     "min": _ffi.MIN, "max": _ffi.MAX, "bitwise_and": _ffi.AND, "bitwise_or": _ffi.OR,
+                     "bitwise_xor": _ffi.XOR, "power": _ffi.POW}
+
+
+def fused_chain_int_op(data, steps, pipeline):
+    """fused_chain_op on an INTEGER column: the running value, the operand columns and the scalars
+    all have the type of `data`; each step is the stand-alone integer kernel of that op (wrap in
+    the column's width, x/0 = x, x%0 = 0).  Steps:
+         ("bitwise_not",)  ("abs",)  [abs: Int32 only]
+         ("add", other) ... sub mul div rem min max bitwise_and bitwise_or bitwise_xor power [Int32]
+         ("gt", other) ... gteq lt lteq eq          (only as the last step) -> BooleanArrayGPU
+    `other` = a column of the same type and length, a DeviceScalar / one-element array of the same
+    type, or a python int (uploaded as a one-element array)."""
+    if not isinstance(data, _INT_TYPES + (Date32ArrayGPU,)):
+        raise Panic(f"fused_chain_int not supported for type {data.get_dtype()}")
+    if not 1 <= len(steps) <= _ffi.CHAIN_MAX_STEPS:
+        raise Panic(f"fused_chain_int takes 1..{_ffi.CHAIN_MAX_STEPS} steps")
+    arr = (_ffi.ChainStep * len(steps))()
+    validities = [data.null_buffer]
+    keep = []           # one-element arrays made here must outlive the launch call
+    is_pred = False
+    for k, step in enumerate(steps):
+        name, operand = step[0], (step[1] if len(step) > 1 else None)
+        if name in ("abs", "power") and not isinstance(data, _I32_BACKED):
+            raise Panic(f"fused_chain_int: {name} not supported for type {data.get_dtype()}")   # math/src/i32.rs
+        if name in _INT_CHAIN_UNARY and operand is None:
+            arr[k].kind, arr[k].op = _ffi.STEP_UNARY, _INT_CHAIN_UNARY[name]
+            continue
+        if name in _INT_CHAIN_BINARY:
+            op, kinds = _INT_CHAIN_BINARY[name], (_ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_DEVSCALAR)
+        elif name in _CHAIN_COMPARE:
+            if k != len(steps) - 1:
+                raise Panic("a compare can only end a fused chain")
+            op, kinds, is_pred = _CHAIN_COMPARE[name], (_ffi.STEP_COMPARE_COLUMN, _ffi.STEP_COMPARE_DEVSCALAR), True
+        else:
+            raise Panic(f"fused_chain_int: unknown step {step!r}")
+        arr[k].op = op
+        if isinstance(operand, (int, np.integer)):
+            operand = DeviceScalar(type(data).from_slice([operand], data.gpu_device))
+            keep.append(operand)
+        if isinstance(operand, DeviceScalar):
+            operand = operand.array
+            scalar = True
+        else:
+            scalar = isinstance(operand, PrimitiveArrayGpu) and operand.len == 1 and data.len != 1
+        if type(operand) is not type(data):
+            raise Panic(f"fused_chain_int: operand of {name!r} must be a {type(data).__name__}")
+        if scalar:
+            arr[k].kind, arr[k].operand = kinds[1], operand.data.ptr
+        else:
+            _check_same_len(data, operand, "fused_chain_int")
+            arr[k].kind, arr[k].operand, arr[k].validity = kinds[0], operand.data.ptr, _vptr(operand.null_buffer)
+            validities.append(operand.null_buffer)
+    dev = data.gpu_device
+    nb = _new_validity(dev, data.len, *validities)
+    out = (BooleanArrayGPU if is_pred else type(data)).empty(data.len, dev, nb)
+    check(lib().agpu_fused_chain_int(dev.handle, data.DTYPE, data.data.ptr, _vptr(data.null_buffer), arr, len(steps),
+                                     out.data.ptr, data.len, _vptr(nb)), "fused_chain_int")
+    return out
+
+
+def fused_chain_int(data, steps):
+    pipeline = _pipeline_for(data)
+    out = fused_chain_int_op(data, steps, pipeline)
+    pipeline.finish()
+    return out
+
+
 # ==========================================================================================
 # auto-fusion: ArrowComputePipeline(device, fuse=True)
 # ==========================================================================================
@@ -776,35 +849,67 @@ _FUSE_COMPARE = set(_CHAIN_COMPARE)
 _MAX_CHAIN_COLS = 3
 
 
+_FUSE_INT_BINARY = {"add", "sub", "mul", "div", "min", "max", "bitwise_and", "bitwise_or", "bitwise_xor"}
+
+
 class _LazyChain:
-    def __init__(self, source, steps, pipeline):
-        self.source, self.steps, self.pipeline, self.consumed = source, steps, pipeline, False
+    """mode "f32": steps of agpu_fused_chain on cast<f32>(source); mode "int": steps of
+    agpu_fused_chain_int in the source's own integer type"""
+
+    def __init__(self, source, steps, pipeline, mode="f32"):
+        self.source, self.steps, self.pipeline, self.mode, self.consumed = source, steps, pipeline, mode, False
 
     def n_cols(self):
-        return sum(1 for st in self.steps if len(st) > 1 and isinstance(st[1], Float32ArrayGPU))
+        return sum(1 for st in self.steps if len(st) > 1 and isinstance(st[1], PrimitiveArrayGpu))
 
     def evaluate(self):
+        if self.mode == "int":
+            return fused_chain_int_op(self.source, self.steps, self.pipeline)
         if not self.steps:      # a bare int -> f32 cast that nothing was chained onto
             return _cast_to(self.source, Float32ArrayGPU, self.pipeline)
         return fused_chain_op(self.source, self.steps, self.pipeline)
 
 
-def _lazy_array(source, steps, pipeline):
-    arr = Float32ArrayGPU(None, source.gpu_device, source.len, None)
-    arr._lazy = _LazyChain(source, steps, pipeline)
+def _lazy_array(source, steps, pipeline, mode="f32"):
+    cls = Float32ArrayGPU if mode == "f32" else type(source)
+    arr = cls(None, source.gpu_device, source.len, None)
+    arr._lazy = _LazyChain(source, steps, pipeline, mode)
     pipeline._lazies.append(weakref.ref(arr))
     return arr
 
 
-def _extend(self, step, pipeline):
+def _extend(self, step, pipeline, mode="f32"):
     """new recorded array = chain of `self` + step (or a fresh chain starting at `self`)"""
     lazy = self._lazy
-    adds_col = len(step) > 1 and isinstance(step[1], Float32ArrayGPU)
-    if (lazy is not None and lazy.pipeline is pipeline and len(lazy.steps) < _ffi.CHAIN_MAX_STEPS
+    adds_col = len(step) > 1 and isinstance(step[1], PrimitiveArrayGpu)
+    if (lazy is not None and lazy.pipeline is pipeline and lazy.mode == mode and len(lazy.steps) < _ffi.CHAIN_MAX_STEPS
             and (not adds_col or lazy.n_cols() < _MAX_CHAIN_COLS)):
         lazy.consumed = True
         return lazy.source, lazy.steps + [step]
     return self, [step]      # `self` (concrete, or launched on demand) becomes the source
+
+
+def _try_fuse_int(base, self, operand, pipeline):
+    """integer columns: wrapping arithmetic, min/max, bitwise logic, scalar ops and a closing
+    compare of ONE integer type record into an agpu_fused_chain_int chain"""
+    if base == "bitwise_not" and operand is None:
+        return _lazy_array(*_extend(self, (base,), pipeline, "int"), pipeline, "int")
+    if base == "abs" and operand is None and isinstance(self, Int32ArrayGPU):
+        return _lazy_array(*_extend(self, (base,), pipeline, "int"), pipeline, "int")
+    if type(operand) is not type(self):
+        return None
+    if base in _FUSE_SCALAR:
+        if operand.len != 1:
+            return None
+        return _lazy_array(*_extend(self, (_FUSE_SCALAR[base], DeviceScalar(operand)), pipeline, "int"), pipeline, "int")
+    if operand.len != self.len:
+        return None
+    if base in _FUSE_INT_BINARY or (base == "power" and isinstance(self, Int32ArrayGPU)):
+        return _lazy_array(*_extend(self, (base, operand), pipeline, "int"), pipeline, "int")
+    if base in _FUSE_COMPARE:
+        source, steps = _extend(self, (base, operand), pipeline, "int")
+        return fused_chain_int_op(source, steps, pipeline)    # a predicate ends the chain: launch now
+    return None
 
 
 def _try_fuse(name, self, args):
@@ -823,7 +928,8 @@ def _try_fuse(name, self, args):
     if base in _FUSE_UNARY and operand is None:
         if is_f32 or (base in ("sin", "cos", "sinh") and isinstance(self, _TRIG_INT)):
             return _lazy_array(*_extend(self, (base,), pipeline), pipeline)
-        return None
+    if isinstance(self, _INT_TYPES):
+        return _try_fuse_int(base, self, operand, pipeline)
     if not is_f32 or not isinstance(operand, Float32ArrayGPU):
         return None
     if base in _FUSE_SCALAR:

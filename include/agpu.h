@@ -241,12 +241,25 @@ typedef enum {
 typedef struct {
   int32_t kind;             /* agpu_step_kind */
   int32_t op;               /* agpu_unop / agpu_binop / agpu_cmpop id */
-  const float* operand;     /* device f32 column for *_COLUMN steps */
+  const void* operand;      /* device column for *_COLUMN steps / one-element array for *_DEVSCALAR steps
+                             * (f32 for agpu_fused_chain, the column type for agpu_fused_chain_int) */
   const uint32_t* validity; /* its validity bitmap or NULL */
   float scalar;             /* immediate for *_SCALAR steps */
 } agpu_chain_step;
 int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, const uint32_t* vin,
                      const agpu_chain_step* steps, int n_steps, void* out, size_t n, uint32_t* vout);
+
+/* The same chain machinery on INTEGER columns (dtype = I8 U8 I16 U16 I32 U32 DATE32): the running
+ * value, every operand column and every device scalar have type `dtype`, and each step is the
+ * stand-alone integer kernel of that op — wrap in the column's own width, x/0 = x, x%0 = 0,
+ * MIN/-1 = MIN, signedness of min/max/compare — so the result is bit-identical to the ops run one
+ * by one (logical/src/lib.rs:120-158, arithmetic/src/lib.rs:11-94, compare/src/lib.rs:142-172).
+ *   AGPU_STEP_UNARY              NOT (ABS for I32)
+ *   AGPU_STEP_BINARY_COLUMN / _DEVSCALAR   ADD SUB MUL DIV REM MIN MAX AND OR XOR (POW for I32)
+ *   AGPU_STEP_COMPARE_COLUMN / _DEVSCALAR  GT GTEQ LT LTEQ EQ, last step only; out is a bitmap
+ * Immediates (*_SCALAR steps) are not accepted: the float field cannot hold every 32-bit integer. */
+int agpu_fused_chain_int(agpu_device* dev, int dtype, const void* in, const uint32_t* vin,
+                         const agpu_chain_step* steps, int n_steps, void* out, size_t n, uint32_t* vout);
 
 /* ---- routines: crates/routines ---- */
 

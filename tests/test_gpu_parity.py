@@ -523,3 +523,108 @@ def test_auto_fusion_launch_counts(device):
     for k in range(11):
         ref = ref * np.float32(0.5) + (b, c, d)[k % 3].raw_values()
     assert same_f32_bits(x.raw_values(), ref)
+
+
+# ---- integer chains (agpu_fused_chain_int) --------------------------------------------------------
+INT_CHAINS = [
+    [("add", "col"), ("bitwise_and", "col"), ("mul", "scalar")],
+    [("bitwise_not",), ("sub", "col"), ("min", "col"), ("max", "col")],
+    [("mul", "col"), ("div", "scalar"), ("rem", "scalar"), ("bitwise_xor", "col"), ("gt", "col")],
+    [("bitwise_or", "scalar"), ("div", "col"), ("lteq", "scalar")],
+    [("rem", "col"), ("eq", "col")],
+]
+
+
+@pytest.mark.parametrize("dtype", list(INT_CLS), ids=lambda d: NAMES[d])
+@pytest.mark.parametrize("chain", range(len(INT_CHAINS)))
+def test_fused_chain_int_equals_unfused_and_oracle(chain, dtype, device):
+    rng = np.random.default_rng(stable_seed("intchain", chain, dtype))
+    for n in (0, 1, 33, 4099, 70001):
+        a, oa = make(rng, dtype, n, True, device)
+        steps, want, o = [], a, oa
+        for step in INT_CHAINS[chain]:
+            name = step[0]
+            if len(step) == 1:
+                want, o = getattr(want, name)(), oracle_unary(name, o)
+                steps.append(step)
+                continue
+            if step[1] == "col":
+                g, og = make(rng, dtype, n, bool(rng.random() < 0.5), device)
+                if name in ("div", "rem") and n > 8:
+                    og.data[7] = 0          # the divide-by-zero rules inside a chain
+                    g = ALL_CLS[dtype].from_numpy(og.data, None if og.valid is None else O.unpack_bits(og.valid, n), device)
+                steps.append((name, g))
+                if name == "rem":            # array % array has no method name in the reference: C ABI id
+                    want = K._binary(ag._ffi.REM, want, g, what="rem")
+                    o = OArr(dtype, O.binary(O.REM, dtype, o.data, og.data), n, O.validity_and(o.valid, og.valid, n))
+                else:
+                    want, o = getattr(want, name)(g), oracle_binary(name, o, og)
+            else:
+                sv = rand_vals(rng, dtype, 1, special=False)
+                if name in ("div", "rem") and rng.random() < 0.3:
+                    sv[0] = 0
+                gs = ALL_CLS[dtype].from_numpy(sv, None, device)
+                steps.append((name, K.DeviceScalar(gs)))
+                if name in ("add", "sub", "mul", "div", "rem"):
+                    want, o = getattr(want, name + "_scalar")(gs), oracle_scalar(name + "_scalar", o, OArr(dtype, sv, 1))
+                else:                        # min/max/logic/compare with a scalar: broadcast column on the unfused side
+                    col = ALL_CLS[dtype].from_numpy(np.full(n, sv[0]), None, device)
+                    ocol = OArr(dtype, np.full(n, sv[0]).astype(O.NP[dtype]), n)
+                    want, o = getattr(want, name)(col), oracle_binary(name, o, ocol)
+        l0 = device.launch_count()
+        got = K.fused_chain_int(a, steps)
+        assert device.launch_count() - l0 == (1 if n else 0)
+        if o.dtype == O.BOOL:
+            words = O.words(n) * 4
+            assert np.array_equal(device.retrive_data(got.data, words), device.retrive_data(want.data, words)), (chain, n)
+            assert np.array_equal(device.retrive_data(got.data, words).view(np.uint32), o.data), (chain, n)
+            assert np.array_equal(device.retrive_data(got.null_buffer.bit_buffer, words).view(np.uint32), o.valid), (chain, n)
+        else:
+            assert_same(got, o, f"int chain {chain} {NAMES[dtype]} n={n}")
+            assert np.array_equal(got.raw_values(), want.raw_values())
+
+
+def test_fused_chain_int_limits(device):
+    a = ag.Int16ArrayGPU.from_slice([1, 2, 3], device)
+    with pytest.raises(ag.Panic):
+        K.fused_chain_int(a, [("gt", a), ("add", a)])
+    with pytest.raises(ag.Panic):
+        K.fused_chain_int(a, [("add", ag.Int8ArrayGPU.from_slice([1, 2, 3], device))])
+    with pytest.raises(ag.Panic):
+        K.fused_chain_int(ag.Float32ArrayGPU.from_slice([1.0], device), [("bitwise_not",)])
+    with pytest.raises(ag.Panic):
+        K.fused_chain_int(a, [("abs",)])                    # abs is an Int32 op (math/src/i32.rs)
+    assert K.fused_chain_int(a, [("add", 5), ("mul", a)]).raw_values().tolist() == [6, 14, 24]
+    i32 = ag.Int32ArrayGPU.from_slice([-3, 2, -2**31], device)
+    assert K.fused_chain_int(i32, [("abs",), ("power", ag.Int32ArrayGPU.from_slice([2, 3, 1], device))]).raw_values().tolist() \
+        == [9, 8, -2**31]
+
+
+def test_auto_fusion_int_chain_launch_counts(device):
+    rng = np.random.default_rng(5)
+    n = 100_001
+    a, b, c = (make(rng, O.U8, n, k == 0, device)[0] for k in range(3))
+    s = ag.UInt8ArrayGPU.from_slice([7], device)
+
+    def program(p):
+        t = K.bitwise_and_op_dyn(K.add_op_dyn(a, b, p), c, p)
+        return K.gt_op_dyn(K.mul_scalar_op_dyn(t, s, p), b, p), t
+
+    plain = ag.ArrowComputePipeline(device)
+    l0 = device.launch_count()
+    want_m, want_t = program(plain)
+    plain.finish()
+    n_plain = device.launch_count() - l0
+    fusing = ag.ArrowComputePipeline(device, fuse=True)
+    l0 = device.launch_count()
+    got_m, got_t = program(fusing)
+    fusing.finish()
+    n_fused = device.launch_count() - l0
+    assert n_plain == 4 and n_fused == 1, (n_plain, n_fused)     # add, and, mul_scalar, gt in ONE kernel
+    words = O.words(n) * 4
+    assert np.array_equal(device.retrive_data(got_m.data, words), device.retrive_data(want_m.data, words))
+    assert np.array_equal(device.retrive_data(got_m.null_buffer.bit_buffer, words),
+                          device.retrive_data(want_m.null_buffer.bit_buffer, words))
+    l0 = device.launch_count()
+    assert np.array_equal(got_t.raw_values(), want_t.raw_values())   # absorbed prefix: launched when read
+    assert device.launch_count() - l0 == 1
