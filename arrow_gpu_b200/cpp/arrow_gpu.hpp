@@ -593,4 +593,53 @@ std::variant<Float32ArrayGPU, BooleanArrayGPU> fused_chain(const PrimitiveArrayG
   return out;
 }
 
+// the same chain on an INTEGER column (agpu_fused_chain_int): operands are columns or one-element
+// device arrays of the column's own type; no immediates
+template <typename T>
+struct IntChainStep {
+  agpu_chain_step raw{};
+  bool has_validity = false;
+  static IntChainStep unary(agpu_unop op) { IntChainStep s; s.raw.kind = AGPU_STEP_UNARY; s.raw.op = op; return s; }
+  static IntChainStep binary(agpu_binop op, const PrimitiveArrayGpu<T>& o, size_t len) { return with(op, o, len, AGPU_STEP_BINARY_COLUMN, AGPU_STEP_BINARY_DEVSCALAR); }
+  static IntChainStep compare(agpu_cmpop op, const PrimitiveArrayGpu<T>& o, size_t len) { return with(op, o, len, AGPU_STEP_COMPARE_COLUMN, AGPU_STEP_COMPARE_DEVSCALAR); }
+ private:
+  static IntChainStep with(int op, const PrimitiveArrayGpu<T>& o, size_t len, int col_kind, int scalar_kind) {
+    IntChainStep s;
+    const bool scalar = o.len == 1 && len != 1;  // len-1 operands are scalars, as in add_dyn (arithmetic_kernels.rs:110-117)
+    if (!scalar && o.len != len) throw Panic("fused_chain_int: length mismatch");
+    s.raw.kind = scalar ? scalar_kind : col_kind;
+    s.raw.op = op;
+    s.raw.operand = o.data->ptr();
+    if (!scalar) { s.raw.validity = vptr(o.null_buffer); s.has_validity = bool(o.null_buffer); }
+    return s;
+  }
+};
+
+template <typename T>
+std::variant<PrimitiveArrayGpu<T>, BooleanArrayGPU> fused_chain_int(const PrimitiveArrayGpu<T>& a, const std::vector<IntChainStep<T>>& steps) {
+  std::vector<agpu_chain_step> raw;
+  bool any_validity = bool(a.null_buffer), pred = false;
+  for (const auto& s : steps) {
+    raw.push_back(s.raw);
+    any_validity = any_validity || s.has_validity;
+    pred = s.raw.kind == AGPU_STEP_COMPARE_COLUMN || s.raw.kind == AGPU_STEP_COMPARE_DEVSCALAR;
+  }
+  Validity nb;
+  if (any_validity) nb = NullBitBufferGpu{std::make_shared<ArrowGpuBuffer>(a.gpu_device, bitmap_words(a.len) * 4), a.len, a.gpu_device};
+  auto launch = [&](void* out, Validity& v) {
+    int rc = agpu_fused_chain_int(a.gpu_device->handle(), PrimitiveArrayGpu<T>::DTYPE, a.data->ptr(), vptr(a.null_buffer), raw.data(),
+                                  (int)raw.size(), out, a.len, vptr_mut(v));
+    if (rc == AGPU_EUNSUPPORTED || rc == AGPU_EINVAL) throw Panic("fused_chain_int: unsupported chain");
+    check(rc, "fused_chain_int");
+  };
+  if (pred) {
+    auto out = BooleanArrayGPU::empty(a.len, a.gpu_device, nb);
+    launch(out.data->ptr(), out.null_buffer);
+    return out;
+  }
+  auto out = PrimitiveArrayGpu<T>::empty(a.len, a.gpu_device, nb);
+  launch(out.data->ptr(), out.null_buffer);
+  return out;
+}
+
 }  // namespace arrow_gpu

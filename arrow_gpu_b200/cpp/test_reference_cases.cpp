@@ -148,6 +148,16 @@ int main() {
     CHECK(std::get<BooleanArrayGPU>(chained).raw_values() == ga.mul(gb).add(gc).gt(gd).raw_values());
     auto chain_vals = fused_chain(Int8ArrayGPU::from_slice({0, 1, 4, 9, -16}, device), {ChainStep::unary(AGPU_ABS), ChainStep::unary(AGPU_SQRT), ChainStep::binary(AGPU_MUL, 2.0f)});
     CHECK(feq(std::get<Float32ArrayGPU>(chain_vals).raw_values(), {0, 2, 4, 6, 8}));
+    // integer chain: ((x + y) & 0x0F) * 3 with u8 wrap, then > y  — one kernel each
+    auto ux = UInt8ArrayGPU::from_slice({250, 7, 16, 255, 0}, device);
+    auto uy = UInt8ArrayGPU::from_slice({10, 9, 16, 1, 0}, device);
+    auto u15 = UInt8ArrayGPU::from_slice({15}, device);
+    auto u3 = UInt8ArrayGPU::from_slice({3}, device);
+    using S8 = IntChainStep<uint8_t>;
+    auto ichain = fused_chain_int(ux, {S8::binary(AGPU_ADD, uy, ux.len), S8::binary(AGPU_AND, u15, ux.len), S8::binary(AGPU_MUL, u3, ux.len)});
+    CHECK((std::get<UInt8ArrayGPU>(ichain).raw_values() == std::vector<uint8_t>{12, 0, 0, 0, 0}));
+    auto ipred = fused_chain_int(ux, {S8::unary(AGPU_NOT), S8::compare(AGPU_GT, uy, ux.len)});
+    CHECK((std::get<BooleanArrayGPU>(ipred).raw_values() == std::vector<bool>{false, true, true, false, true}));
     auto vals = Int32ArrayGPU::from_optional_slice({10, None, 30, 40, 50, 60}, device);
     auto keep = BooleanArrayGPU::from_optional_slice({true, true, false, None, true, false}, device);
     std::vector<Opt<int32_t>> want = {10, None, 50};

@@ -3,9 +3,10 @@
 // Every step applies the same functor as the stand-alone integer kernel of that op (ops.cuh:
 // two's-complement wrap in the column's own width, the WGSL divide/remainder-by-zero rules,
 // signedness of min/max/compare), so a fused chain is bit-identical to the ops run one by one.
-// Rows move as 16-byte granules of the column type (16 x i8, 8 x i16, 4 x i32); operand columns
-// stay packed in their load registers until the step that consumes them (steps consume the
-// columns in order, so the "next column" is always slot 0 and the slots rotate).
+// Rows move as 16-byte granules of the column type (16 x i8, 8 x i16, 4 x i32) and STAY packed:
+// the running value of a granule is four 32-bit words, narrow lanes are processed SIMD-in-word
+// where the op allows it.  Steps consume the operand columns in order, so the "next column" is
+// always slot 0 and the slots rotate.
 #include "bits.cuh"
 #include "elementwise.cuh"
 #include "ops.cuh"
@@ -23,59 +24,107 @@ struct IntChainProgram {
   const void* cols[kMaxCols];
 };
 
+// ---- packed words: a 16-byte granule is four 32-bit words of L = 4/sizeof(T) lanes each --------
+// add/sub/min/max/compare run on whole words (SIMD-in-word), and/or/xor/not are plain word ops;
+// mul/div/rem/pow unpack the lanes, apply the stand-alone functor and repack.
+template <typename T, template <typename> class F>
+__device__ __forceinline__ uint32_t lanewise(uint32_t a, uint32_t b) {
+  constexpr int L = 4 / sizeof(T), B = 8 * sizeof(T);
+  if constexpr (L == 1) {
+    return (uint32_t)F<T>{}((T)a, (T)b);
+  } else {
+    using UT = typename std::make_unsigned<T>::type;
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < L; ++k)
+      r |= (uint32_t)(UT)F<T>{}((T)(UT)(a >> (B * k)), (T)(UT)(b >> (B * k))) << (B * k);
+    return r;
+  }
+}
+template <typename T> __device__ __forceinline__ uint32_t w_add(uint32_t a, uint32_t b) {
+  if constexpr (sizeof(T) == 1) return __vadd4(a, b);
+  else if constexpr (sizeof(T) == 2) return __vadd2(a, b);
+  else return a + b;
+}
+template <typename T> __device__ __forceinline__ uint32_t w_sub(uint32_t a, uint32_t b) {
+  if constexpr (sizeof(T) == 1) return __vsub4(a, b);
+  else if constexpr (sizeof(T) == 2) return __vsub2(a, b);
+  else return a - b;
+}
+template <typename T> __device__ __forceinline__ uint32_t w_min(uint32_t a, uint32_t b) {
+  if constexpr (sizeof(T) < 4) return OpMin<T>::word(a, b);
+  else return (uint32_t)OpMin<T>{}((T)a, (T)b);
+}
+template <typename T> __device__ __forceinline__ uint32_t w_max(uint32_t a, uint32_t b) {
+  if constexpr (sizeof(T) < 4) return OpMax<T>::word(a, b);
+  else return (uint32_t)OpMax<T>{}((T)a, (T)b);
+}
+template <typename T> __device__ __forceinline__ uint32_t w_splat(T v) {  // the scalar in every lane
+  using UT = typename std::make_unsigned<T>::type;
+  if constexpr (sizeof(T) == 1) return (uint32_t)(UT)v * 0x01010101u;
+  else if constexpr (sizeof(T) == 2) return (uint32_t)(UT)v * 0x00010001u;
+  else return (uint32_t)v;
+}
+
 template <typename T, int N>
-__device__ __forceinline__ void int_unary(int op, T (&a)[N]) {
+__device__ __forceinline__ void words_unary(int op, uint32_t (&a)[N]) {
   if (op == AGPU_NOT) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) a[k] = OpNot<T>{}(a[k]);
+    for (int k = 0; k < N; ++k) a[k] = ~a[k];
   } else if constexpr (std::is_same<T, int32_t>::value) {  // AGPU_ABS (int32 only, checked on the host)
 #pragma unroll
-    for (int k = 0; k < N; ++k) a[k] = OpAbs<T>{}(a[k]);
+    for (int k = 0; k < N; ++k) a[k] = (uint32_t)OpAbs<T>{}((T)a[k]);
   }
 }
 
 template <typename T, int N>
-__device__ __forceinline__ void int_binary(int op, T (&a)[N], const T (&b)[N]) {
-#define BN(F)                                                                  \
-  _Pragma("unroll") for (int k = 0; k < N; ++k) a[k] = F<T>{}(a[k], b[k]); \
+__device__ __forceinline__ void words_binary(int op, uint32_t (&a)[N], const uint32_t (&b)[N]) {
+#define BW(EXPR)                                                \
+  _Pragma("unroll") for (int k = 0; k < N; ++k) a[k] = EXPR; \
   break;
   switch (op) {
-    case AGPU_ADD: BN(OpAdd)
-    case AGPU_SUB: BN(OpSub)
-    case AGPU_MUL: BN(OpMul)
-    case AGPU_DIV: BN(OpDiv)
-    case AGPU_REM: BN(OpRem)
-    case AGPU_MIN: BN(OpMin)
-    case AGPU_MAX: BN(OpMax)
-    case AGPU_AND: BN(OpAnd)
-    case AGPU_OR: BN(OpOr)
-    case AGPU_XOR: BN(OpXor)
+    case AGPU_ADD: BW(w_add<T>(a[k], b[k]))
+    case AGPU_SUB: BW(w_sub<T>(a[k], b[k]))
+    case AGPU_MUL: BW((lanewise<T, OpMul>(a[k], b[k])))
+    case AGPU_DIV: BW((lanewise<T, OpDiv>(a[k], b[k])))
+    case AGPU_REM: BW((lanewise<T, OpRem>(a[k], b[k])))
+    case AGPU_MIN: BW(w_min<T>(a[k], b[k]))
+    case AGPU_MAX: BW(w_max<T>(a[k], b[k]))
+    case AGPU_AND: BW(a[k] & b[k])
+    case AGPU_OR: BW(a[k] | b[k])
+    case AGPU_XOR: BW(a[k] ^ b[k])
     case AGPU_POW:
       if constexpr (std::is_same<T, int32_t>::value) {
-        BN(OpPow)
+        BW((lanewise<T, OpPow>(a[k], b[k])))
       }
       break;
     default: break;
   }
-#undef BN
+#undef BW
 }
 
-template <typename T, int N>
-__device__ __forceinline__ uint32_t int_compare(int op, const T (&a)[N], const T (&b)[N]) {
+// predicate bits of NG granules (4 words each): G bits per granule, granule j at bit j*G
+template <typename T, class P, int N>
+__device__ __forceinline__ uint32_t words_pred(const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+  constexpr int L = 4 / sizeof(T);
   uint32_t m = 0;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    bool p;
-    switch (op) {
-      case AGPU_GT: p = a[k] > b[k]; break;
-      case AGPU_GTEQ: p = a[k] >= b[k]; break;
-      case AGPU_LT: p = a[k] < b[k]; break;
-      case AGPU_LTEQ: p = a[k] <= b[k]; break;
-      default: p = a[k] == b[k]; break;
-    }
-    m |= (uint32_t)p << k;
+    if constexpr (sizeof(T) == 1) m |= (((P::template lanes<T>(a[k], b[k]) & 0x08040201u) * 0x01010101u) >> 24) << (L * k);
+    else if constexpr (sizeof(T) == 2) m |= ((((P::template lanes<T>(a[k], b[k]) & 0x00020001u) * 0x00010001u) >> 16) & 3u) << (L * k);
+    else m |= (uint32_t)P{}((T)a[k], (T)b[k]) << k;
   }
   return m;
+}
+template <typename T, int N>
+__device__ __forceinline__ uint32_t words_compare(int op, const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+  switch (op) {
+    case AGPU_GT: return words_pred<T, PGt, N>(a, b);
+    case AGPU_GTEQ: return words_pred<T, PGe, N>(a, b);
+    case AGPU_LT: return words_pred<T, PLt, N>(a, b);
+    case AGPU_LTEQ: return words_pred<T, PLe, N>(a, b);
+    default: return words_pred<T, PEq, N>(a, b);
+  }
 }
 
 template <typename T>
@@ -84,27 +133,28 @@ struct IntChainOp {
   IntChainProgram p;
   const T* in;
   T* out;  // value chains only
-  struct In { Vec<T, G> a; Vec<T, G> c[kMaxCols]; };
+  struct In { uint4 a; uint4 c[kMaxCols]; };
 
+  static __device__ __forceinline__ uint4 ld16(const T* base, size_t g) {
+    return __ldcs(reinterpret_cast<const uint4*>(base) + g);
+  }
   __device__ __forceinline__ In load(size_t g) const {
     In r;
-    r.a = ld_vec<T, G>(in, g);
+    r.a = ld16(in, g);
 #pragma unroll
     for (int k = 0; k < kMaxCols; ++k)
-      if (k < p.n_cols) r.c[k] = ld_vec<T, G>((const T*)p.cols[k], g);
+      if (k < p.n_cols) r.c[k] = ld16((const T*)p.cols[k], g);
     return r;
   }
-  // 32-bit rows: two granules (8 accumulators) share one pass over the steps; narrower rows
-  // already have 8 or 16 accumulators per granule
-  static constexpr bool JOINT = sizeof(T) == 4;
+  static constexpr bool JOINT = true;  // all granules of a full tile share one pass over the steps
 
+  // acc / rhs: 4 words per granule
   template <int U>
-  __device__ __forceinline__ void eval(const In (&inu)[U], T (&acc)[G * U], T (&rhs)[G * U], int& cmp_op) const {
-    Vec<T, G> cc[U][kMaxCols];
+  __device__ __forceinline__ void eval(const In (&inu)[U], uint32_t (&acc)[4 * U], uint32_t (&rhs)[4 * U], int& cmp_op) const {
+    uint4 cc[U][kMaxCols];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-#pragma unroll
-      for (int k = 0; k < G; ++k) acc[j * G + k] = inu[j].a.e[k];
+      acc[4 * j] = inu[j].a.x; acc[4 * j + 1] = inu[j].a.y; acc[4 * j + 2] = inu[j].a.z; acc[4 * j + 3] = inu[j].a.w;
 #pragma unroll
       for (int c = 0; c < kMaxCols; ++c) cc[j][c] = inu[j].c[c];
     }
@@ -113,95 +163,96 @@ struct IntChainOp {
     for (int s = 0; s < p.n_steps; ++s) {
       const int kind = p.kind[s];
       if (kind == AGPU_STEP_UNARY) {
-        int_unary<T, G * U>(p.op[s], acc);
+        words_unary<T, 4 * U>(p.op[s], acc);
         continue;
       }
       if (kind == AGPU_STEP_BINARY_DEVSCALAR || kind == AGPU_STEP_COMPARE_DEVSCALAR) {
-        const T v = __ldg((const T*)p.dscalar[s]);
+        const uint32_t v = w_splat<T>(__ldg((const T*)p.dscalar[s]));
 #pragma unroll
-        for (int k = 0; k < G * U; ++k) rhs[k] = v;
+        for (int k = 0; k < 4 * U; ++k) rhs[k] = v;
       } else {  // next operand column: slot 0, then the slots move up
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-#pragma unroll
-          for (int k = 0; k < G; ++k) rhs[j * G + k] = cc[j][0].e[k];
+          rhs[4 * j] = cc[j][0].x; rhs[4 * j + 1] = cc[j][0].y; rhs[4 * j + 2] = cc[j][0].z; rhs[4 * j + 3] = cc[j][0].w;
           cc[j][0] = cc[j][1];
           cc[j][1] = cc[j][2];
         }
       }
       if (kind == AGPU_STEP_BINARY_COLUMN || kind == AGPU_STEP_BINARY_DEVSCALAR)
-        int_binary<T, G * U>(p.op[s], acc, rhs);
+        words_binary<T, 4 * U>(p.op[s], acc, rhs);
       else cmp_op = p.op[s];  // compare is the last step (checked on the host)
     }
   }
   template <int U>
   __device__ __forceinline__ void run_joint(size_t g0, const In (&inu)[U]) const {
-    T acc[G * U], rhs[G * U];
+    uint32_t acc[4 * U], rhs[4 * U];
     int cmp;
     eval<U>(inu, acc, rhs, cmp);
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      Vec<T, G> o;
-#pragma unroll
-      for (int k = 0; k < G; ++k) o.e[k] = acc[j * G + k];
-      st_vec<T, G>(out, g0 + (size_t)j * kBlock, o);
-    }
+    for (int j = 0; j < U; ++j)
+      __stcs(reinterpret_cast<uint4*>(out) + g0 + (size_t)j * kBlock,
+             make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
   }
   template <int U>
   __device__ __forceinline__ void bits_joint(size_t, const In (&inu)[U], uint32_t (&b)[U]) const {
-    T acc[G * U], rhs[G * U];
+    uint32_t acc[4 * U], rhs[4 * U];
     int cmp;
     eval<U>(inu, acc, rhs, cmp);
-    const uint32_t m = int_compare<T, G * U>(cmp, acc, rhs);
+    // words_compare packs L bits per word, 4 words per granule: granule j at bit j*G
+    if constexpr (G * U <= 32) {
+      const uint32_t m = words_compare<T, 4 * U>(cmp, acc, rhs);
 #pragma unroll
-    for (int j = 0; j < U; ++j) b[j] = (m >> (G * j)) & ((1u << G) - 1u);
+      for (int j = 0; j < U; ++j) b[j] = (m >> (G * j)) & (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u));
+    } else {
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const uint32_t a4[4] = {acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]};
+        const uint32_t r4[4] = {rhs[4 * j], rhs[4 * j + 1], rhs[4 * j + 2], rhs[4 * j + 3]};
+        b[j] = words_compare<T, 4>(cmp, a4, r4);
+      }
+    }
   }
-  __device__ __forceinline__ void eval1(const In& in1, T (&acc)[G], T (&rhs)[G], int& cmp_op) const {
+  __device__ __forceinline__ void eval1(const In& in1, uint32_t (&acc)[4], uint32_t (&rhs)[4], int& cmp_op) const {
     const In one[1] = {in1};
     eval<1>(one, acc, rhs, cmp_op);
   }
   __device__ __forceinline__ In load_row(size_t i) const {  // one row replicated over a granule
     In r;
-    const T v = in[i];
-#pragma unroll
-    for (int k = 0; k < G; ++k) r.a.e[k] = v;
+    const uint32_t v = w_splat<T>(in[i]);
+    r.a = make_uint4(v, v, v, v);
 #pragma unroll
     for (int c = 0; c < kMaxCols; ++c)
       if (c < p.n_cols) {
-        const T w = ((const T*)p.cols[c])[i];
-#pragma unroll
-        for (int k = 0; k < G; ++k) r.c[c].e[k] = w;
+        const uint32_t w = w_splat<T>(((const T*)p.cols[c])[i]);
+        r.c[c] = make_uint4(w, w, w, w);
       }
     return r;
   }
   // ---- value chain: elementwise Op interface
   __device__ __forceinline__ void run(size_t g, const In& in1) const {
-    T acc[G], rhs[G];
+    uint32_t acc[4], rhs[4];
     int cmp;
     eval1(in1, acc, rhs, cmp);
-    Vec<T, G> o;
-#pragma unroll
-    for (int k = 0; k < G; ++k) o.e[k] = acc[k];
-    st_vec<T, G>(out, g, o);
+    __stcs(reinterpret_cast<uint4*>(out) + g, make_uint4(acc[0], acc[1], acc[2], acc[3]));
   }
   __device__ __forceinline__ void tail(size_t i) const {
-    T acc[G], rhs[G];
+    uint32_t acc[4], rhs[4];
     int cmp;
     eval1(load_row(i), acc, rhs, cmp);
-    out[i] = acc[0];
+    out[i] = (T)acc[0];
   }
   // ---- predicate chain: BitsOp interface
   __device__ __forceinline__ uint32_t bits(size_t, const In& in1) const {
-    T acc[G], rhs[G];
+    uint32_t acc[4], rhs[4];
     int cmp;
     eval1(in1, acc, rhs, cmp);
-    return int_compare<T, G>(cmp, acc, rhs);
+    return words_compare<T, 4>(cmp, acc, rhs);
   }
   __device__ __forceinline__ bool bit_at(size_t i) const {
-    T acc[G], rhs[G];
+    uint32_t acc[4], rhs[4];
     int cmp;
     eval1(load_row(i), acc, rhs, cmp);
-    return int_compare<T, G>(cmp, acc, rhs) & 1u;
+    return words_compare<T, 4>(cmp, acc, rhs) & 1u;
   }
 };
 

@@ -187,3 +187,23 @@ template <typename TI, typename TO> struct OpCast {
     }
   }
 };
+
+// ---- compare predicates: compare/compute_shaders/*/cmp.wgsl ----
+// Each predicate also knows how to compare a packed word of 8- or 16-bit lanes at once (SIMD-in-
+// word video intrinsics): the result has 0xFF / 0xFFFF in every lane where the predicate holds.
+#define AGPU_PRED(NAME, EXPR, S4, U4, S2, U2)                                                        \
+  struct NAME {                                                                                      \
+    template <typename T> __device__ __forceinline__ bool operator()(T a, T b) const { return EXPR; } \
+    template <typename T> static __device__ __forceinline__ uint32_t lanes(uint32_t a, uint32_t b) {  \
+      if constexpr (std::is_same<T, int8_t>::value) return S4(a, b);                                 \
+      else if constexpr (std::is_same<T, uint8_t>::value) return U4(a, b);                           \
+      else if constexpr (std::is_same<T, int16_t>::value) return S2(a, b);                           \
+      else return U2(a, b);                                                                          \
+    }                                                                                                \
+  };
+AGPU_PRED(PGt, a > b, __vcmpgts4, __vcmpgtu4, __vcmpgts2, __vcmpgtu2)
+AGPU_PRED(PGe, a >= b, __vcmpges4, __vcmpgeu4, __vcmpges2, __vcmpgeu2)
+AGPU_PRED(PLt, a < b, __vcmplts4, __vcmpltu4, __vcmplts2, __vcmpltu2)
+AGPU_PRED(PLe, a <= b, __vcmples4, __vcmpleu4, __vcmples2, __vcmpleu2)
+AGPU_PRED(PEq, a == b, __vcmpeq4, __vcmpeq4, __vcmpeq2, __vcmpeq2)
+#undef AGPU_PRED

@@ -1,0 +1,54 @@
+"""probe (not a test): fused integer chains vs the same ops one kernel each, 256 Mi rows"""
+import os
+import sys
+
+sys.path.insert(0, os.getcwd())
+import torch
+
+import arrow_gpu_b200 as ag
+from arrow_gpu_b200 import kernels as K
+
+dev = ag.GpuDevice(0)
+n = 1 << 28
+g = torch.Generator(device="cuda").manual_seed(5)
+PEAK = 6541.1
+
+
+def column(cls, tdt):
+    t = torch.randint(-100, 100, (n,), dtype=torch.int32, device="cuda", generator=g).to(tdt)
+    return t, cls(ag.ArrowGpuBuffer(dev, t.data_ptr(), t.numel() * t.element_size(), owned=False), dev, n, None)
+
+
+def timeit(fn, reps=5):
+    fn()
+    dev.sync()
+    ts = []
+    for _ in range(reps):
+        e0 = dev.record_event()
+        out = fn()
+        e1 = dev.record_event()
+        dev.sync()
+        ts.append(e0.elapsed_ms(e1))
+        del out
+    return min(ts)
+
+
+for name, cls, tdt, es in (("i8", ag.Int8ArrayGPU, torch.int8, 1), ("u16", ag.UInt16ArrayGPU, torch.int16, 2),
+                           ("i32", ag.Int32ArrayGPU, torch.int32, 4)):
+    keep = [column(cls, tdt) for _ in range(3)]
+    a, b, c = (k[1] for k in keep)
+    s = cls.from_slice([3], dev)
+    chains = {
+        "add b, and c, mul s": ([("add", b), ("bitwise_and", c), ("mul", K.DeviceScalar(s))],
+                                lambda: a.add(b).bitwise_and(c).mul_scalar(s), 4 * es),
+        "not, add s, xor b": ([("bitwise_not",), ("add", K.DeviceScalar(s)), ("bitwise_xor", b)],
+                              lambda: a.bitwise_not().add_scalar(s).bitwise_xor(b), 3 * es),
+        "mul b, add c, gt b": ([("mul", b), ("add", c), ("gt", b)],
+                               lambda: a.mul(b).add(c).gt(b), 3 * es + 0.125),
+    }
+    for label, (steps, unfused, bpr) in chains.items():
+        tf = timeit(lambda: K.fused_chain_int(a, steps))
+        tu = timeit(unfused)
+        print(f"{name:4s} [{label:22s}] fused {tf:.4f} ms ({bpr * n / tf / 1e6:7.1f} GB/s, frac {bpr * n / tf / 1e6 / PEAK:.3f})"
+              f"   unfused {tu:.4f} ms   speed-up {tu / tf:.2f}x")
+    del keep, a, b, c
