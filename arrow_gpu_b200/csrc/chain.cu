@@ -220,7 +220,8 @@ int run_chain(agpu_device* dev, const ChainProgram& p, const void* in, void* out
   bool al = aligned16(in) && aligned16(out);
   for (int k = 0; k < p.n_cols; ++k) al = al && aligned16(p.cols[k]);
   // two granules per thread evaluated jointly: 64 registers, 0.80-0.93 of peak; four (126
-  // registers) measured 30 % slower
+  // registers) measured 30 % slower.  Specialising on the number of operand columns (as
+  // chain_int.cu does, where it lifts 0.70 to 0.93-1.09) measured no gain here (-1 % .. +3 %).
   if (is_pred) return launch_bits<ChainOp<TI>, 2>(dev, op, (uint32_t*)out, n, bm, al);
   return launch_ew<ChainOp<TI>, 2>(dev, op, n, bm, al);
 }

@@ -127,13 +127,16 @@ __device__ __forceinline__ uint32_t words_compare(int op, const uint32_t (&a)[N]
   }
 }
 
-template <typename T>
+// NC = number of operand columns of the chain: the granules of unused column slots would
+// otherwise still occupy registers (16 per slot with two granules in flight)
+template <typename T, int NC>
 struct IntChainOp {
   static constexpr int G = 16 / sizeof(T);
+  static constexpr int NCA = NC ? NC : 1;
   IntChainProgram p;
   const T* in;
   T* out;  // value chains only
-  struct In { uint4 a; uint4 c[kMaxCols]; };
+  struct In { uint4 a; uint4 c[NCA]; };
 
   static __device__ __forceinline__ uint4 ld16(const T* base, size_t g) {
     return __ldcs(reinterpret_cast<const uint4*>(base) + g);
@@ -142,8 +145,7 @@ struct IntChainOp {
     In r;
     r.a = ld16(in, g);
 #pragma unroll
-    for (int k = 0; k < kMaxCols; ++k)
-      if (k < p.n_cols) r.c[k] = ld16((const T*)p.cols[k], g);
+    for (int k = 0; k < NC; ++k) r.c[k] = ld16((const T*)p.cols[k], g);
     return r;
   }
   static constexpr bool JOINT = true;  // all granules of a full tile share one pass over the steps
@@ -151,12 +153,12 @@ struct IntChainOp {
   // acc / rhs: 4 words per granule
   template <int U>
   __device__ __forceinline__ void eval(const In (&inu)[U], uint32_t (&acc)[4 * U], uint32_t (&rhs)[4 * U], int& cmp_op) const {
-    uint4 cc[U][kMaxCols];
+    uint4 cc[U][NCA];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       acc[4 * j] = inu[j].a.x; acc[4 * j + 1] = inu[j].a.y; acc[4 * j + 2] = inu[j].a.z; acc[4 * j + 3] = inu[j].a.w;
 #pragma unroll
-      for (int c = 0; c < kMaxCols; ++c) cc[j][c] = inu[j].c[c];
+      for (int c = 0; c < NC; ++c) cc[j][c] = inu[j].c[c];
     }
     cmp_op = -1;
 #pragma unroll 1
@@ -170,12 +172,12 @@ struct IntChainOp {
         const uint32_t v = w_splat<T>(__ldg((const T*)p.dscalar[s]));
 #pragma unroll
         for (int k = 0; k < 4 * U; ++k) rhs[k] = v;
-      } else {  // next operand column: slot 0, then the slots move up
+      } else if constexpr (NC > 0) {  // next operand column: slot 0, then the slots move up
 #pragma unroll
         for (int j = 0; j < U; ++j) {
           rhs[4 * j] = cc[j][0].x; rhs[4 * j + 1] = cc[j][0].y; rhs[4 * j + 2] = cc[j][0].z; rhs[4 * j + 3] = cc[j][0].w;
-          cc[j][0] = cc[j][1];
-          cc[j][1] = cc[j][2];
+#pragma unroll
+          for (int c = 0; c + 1 < NC; ++c) cc[j][c] = cc[j][c + 1];
         }
       }
       if (kind == AGPU_STEP_BINARY_COLUMN || kind == AGPU_STEP_BINARY_DEVSCALAR)
@@ -221,11 +223,10 @@ struct IntChainOp {
     const uint32_t v = w_splat<T>(in[i]);
     r.a = make_uint4(v, v, v, v);
 #pragma unroll
-    for (int c = 0; c < kMaxCols; ++c)
-      if (c < p.n_cols) {
-        const uint32_t w = w_splat<T>(((const T*)p.cols[c])[i]);
-        r.c[c] = make_uint4(w, w, w, w);
-      }
+    for (int c = 0; c < NC; ++c) {
+      const uint32_t w = w_splat<T>(((const T*)p.cols[c])[i]);
+      r.c[c] = make_uint4(w, w, w, w);
+    }
     return r;
   }
   // ---- value chain: elementwise Op interface
@@ -256,14 +257,25 @@ struct IntChainOp {
   }
 };
 
+template <typename T, int NC>
+int run_int_chain_nc(agpu_device* dev, const IntChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm,
+                     bool is_pred) {
+  IntChainOp<T, NC> op{p, (const T*)in, (T*)out};
+  bool al = aligned16(in) && aligned16(out);
+  for (int k = 0; k < p.n_cols; ++k) al = al && aligned16(p.cols[k]);
+  if (is_pred) return launch_bits<IntChainOp<T, NC>, 2>(dev, op, (uint32_t*)out, n, bm, al);
+  return launch_ew<IntChainOp<T, NC>, 2>(dev, op, n, bm, al);
+}
+
 template <typename T>
 int run_int_chain(agpu_device* dev, const IntChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm,
                   bool is_pred) {
-  IntChainOp<T> op{p, (const T*)in, (T*)out};
-  bool al = aligned16(in) && aligned16(out);
-  for (int k = 0; k < p.n_cols; ++k) al = al && aligned16(p.cols[k]);
-  if (is_pred) return launch_bits<IntChainOp<T>, 2>(dev, op, (uint32_t*)out, n, bm, al);
-  return launch_ew<IntChainOp<T>, 2>(dev, op, n, bm, al);
+  switch (p.n_cols) {
+    case 0: return run_int_chain_nc<T, 0>(dev, p, in, out, n, bm, is_pred);
+    case 1: return run_int_chain_nc<T, 1>(dev, p, in, out, n, bm, is_pred);
+    case 2: return run_int_chain_nc<T, 2>(dev, p, in, out, n, bm, is_pred);
+    default: return run_int_chain_nc<T, 3>(dev, p, in, out, n, bm, is_pred);
+  }
 }
 
 }  // namespace
