@@ -234,6 +234,24 @@ def run(args, rank, world, local_rank, helpers):
             ("i8.filter s=0.5", 1.125 + 0.5, n, lambda: i8a.filter(m)), ("u16.filter s=0.5", 2.125 + 1, n, lambda: u16a.filter(m)),
             ("f32.filter s=0.5 (+validity)", 4.25 + 2.0625, n, lambda: f[0].filter(m)),
         ]
+        # fused integer chains (agpu_fused_chain_int) and the same ops one kernel each
+        from arrow_gpu_b200 import kernels as K
+        sc8 = ag.Int8ArrayGPU.from_slice([3], dev)
+        sc16 = ag.UInt16ArrayGPU.from_slice([3], dev)
+        i8c = sub(torch.int8, ag.Int8ArrayGPU)
+        i32c = _wrap(ag, ag.Int32ArrayGPU, _randint32(torch, n, 95 + seed, tdev), n, dev, keep)
+        i32d = _wrap(ag, ag.Int32ArrayGPU, _randint32(torch, n, 96 + seed, tdev), n, dev, keep)
+        ops += [
+            ("i8 chain [add b, and c, mul s] fused", 4, n,
+             lambda: K.fused_chain_int(i8a, [("add", i8b), ("bitwise_and", i8c), ("mul", K.DeviceScalar(sc8))])),
+            ("i8 chain [add b, and c, mul s] unfused (3 kernels)", 8, n, lambda: i8a.add(i8b).bitwise_and(i8c).mul_scalar(sc8)),
+            ("u16 chain [not, add s, xor b] fused", 6, n,
+             lambda: K.fused_chain_int(u16a, [("bitwise_not",), ("add", K.DeviceScalar(sc16)), ("bitwise_xor", u16b)])),
+            ("u16 chain [not, add s, xor b] unfused (3 kernels)", 14, n, lambda: u16a.bitwise_not().add_scalar(sc16).bitwise_xor(u16b)),
+            ("i32 chain [mul b, add c, gt d] fused", 16.125, n,
+             lambda: K.fused_chain_int(i32[0], [("mul", i32[1]), ("add", i32c), ("gt", i32d)])),
+            ("i32 chain [mul b, add c, gt d] unfused (3 kernels)", 32.125, n, lambda: i32[0].mul(i32[1]).add(i32c).gt(i32d)),
+        ]
     elif name == "sweep":
         # column-size sweep of one binary op with validity (f32 add, 12.375 B/row) from the
         # reference's test sizes up to 1 Gi rows: where launch latency ends and HBM begins.
