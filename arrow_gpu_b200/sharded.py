@@ -128,6 +128,110 @@ def sharded_filter(array, mask):
     return out, offsets[rank], total
 
 
+# ------------------------------------------------------------------------------------------
+# reductions over all shards (local partial -> one tiny exchange)
+# ------------------------------------------------------------------------------------------
+def combine_partial_sums(partials, np_dtype):
+    """The global sum is DEFINED as the left fold, in rank order, of the per-shard sums in the
+    column's own type: f32 = sequential f32 additions (each shard's partial already follows the
+    reference's 256-wide pairwise tree, aggregate.wgsl:28-37), i32/u32 = wrapping.  Every rank
+    computes the same value from the same gathered partials — no dependence on the collective's
+    reduction order."""
+    import numpy as np
+    dt = np.dtype(np_dtype)
+    if dt.kind == "f":
+        acc = dt.type(0)
+        for v in partials:
+            acc = dt.type(acc + dt.type(v))
+        return acc
+    bits = dt.itemsize * 8
+    total = sum(int(v) for v in partials) & ((1 << bits) - 1)
+    if dt.kind == "i" and total >= 1 << (bits - 1):
+        total -= 1 << bits
+    return dt.type(total)
+
+
+def gather_words(local_word: int, device=None) -> List[int]:
+    """all-gather one 32-bit pattern per rank (host value in, list of every rank's value out)"""
+    dist = _dist()
+    if dist is None:
+        return [int(local_word)]
+    import torch
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    mine = torch.tensor([int(local_word)], dtype=torch.int64, device=dev)
+    gathered = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, mine)
+    return [int(t.item()) for t in gathered]
+
+
+def _device_word_gather(dev, fill):
+    """NCCL path shared by the reductions: `fill(ptr)` enqueues a kernel that writes this rank's
+    32-bit partial at device address `ptr`; the all-gather runs on the SAME stream and one
+    4*world-byte readback returns every rank's partial (a single host synchronisation)."""
+    import numpy as np
+    import torch
+    dist = _dist()
+    world = dist.get_world_size()
+    key = (id(dev), "words")
+    ctx = _EXCHANGE_CTX.get(key)
+    if ctx is None:
+        tdev = torch.device("cuda", dev.ordinal)
+        ctx = (torch.cuda.ExternalStream(dev.stream_ptr, device=tdev),
+               torch.zeros(1, dtype=torch.int32, device=tdev), torch.zeros(world, dtype=torch.int32, device=tdev),
+               torch.zeros(world, dtype=torch.int32).pin_memory())
+        torch.cuda.synchronize(tdev)
+        _EXCHANGE_CTX[key] = ctx
+    ext, mine, gathered, host = ctx
+    with torch.cuda.stream(ext):
+        fill(mine.data_ptr())
+        dist.all_gather_into_tensor(gathered, mine)
+        host.copy_(gathered, non_blocking=True)
+        ext.synchronize()
+        return host.numpy().view(np.uint32).copy()
+
+
+def sharded_sum(array):
+    """Sum over ALL shards of a row-range-sharded f32/i32/u32 column (numpy scalar of the column's
+    type, identical on every rank): agpu_sum on the shard, all-gather of the 4-byte partials,
+    rank-ordered fold (combine_partial_sums)."""
+    import numpy as np
+    from . import _ffi
+    dist = _dist()
+    np_dtype = array.NP
+    if dist is not None and dist.get_backend() == "nccl":
+        dev = array.gpu_device
+        words = _device_word_gather(dev, lambda ptr: _ffi.check(
+            _ffi.lib().agpu_sum(dev.handle, array.DTYPE, array.data.ptr, array.len, ptr), "sum"))
+        return combine_partial_sums(words.view(np_dtype), np_dtype)
+    local = array.sum().raw_values()          # one-element array (Sum::sum, aggregate_kernels.rs:24-52)
+    word = int(np.asarray(local, dtype=np_dtype).view(np.uint32)[0])
+    words = np.array(gather_words(word), dtype=np.uint32)
+    return combine_partial_sums(words.view(np_dtype), np_dtype)
+
+
+def _sharded_flag(bits, fn_name, combine):
+    import numpy as np
+    from . import _ffi
+    dist = _dist()
+    if dist is not None and dist.get_backend() == "nccl":
+        dev = bits.gpu_device
+        words = _device_word_gather(dev, lambda ptr: _ffi.check(
+            getattr(_ffi.lib(), fn_name)(dev.handle, bits.data.ptr, bits.len, ptr), fn_name))
+        return bool(combine(int(w) for w in words))
+    local = int(getattr(bits, fn_name[len("agpu_"):])())
+    return bool(combine(gather_words(local)))
+
+
+def sharded_any(bits) -> bool:
+    """LogicalContains::any over all shards of a sharded BooleanArrayGPU"""
+    return _sharded_flag(bits, "agpu_any", max)
+
+
+def sharded_all(bits) -> bool:
+    """LogicalContains::all over all shards (an empty shard counts as all-true)"""
+    return _sharded_flag(bits, "agpu_all", min)
+
+
 class ShardedColumn:
     """One column split into contiguous row ranges, one shard per rank/GPU, with every shard
     mapped into every process (CUDA IPC) so kernels can read peer shards directly over NVLink.

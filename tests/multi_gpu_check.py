@@ -56,6 +56,22 @@ def main():
     t[offset:offset + len(got)] = torch.from_numpy(got).to(t.device)
     dist.all_reduce(t)
     assert np.array_equal(t[:total].cpu().numpy(), want)
+    # reductions over all shards: per-shard partial on the device, one all-gather, rank-ordered fold
+    partials = [vals[slice(*sharded.row_range(n, r, world))].astype(np.int64).sum() for r in range(world)]
+    assert sharded.sharded_sum(a) == np.int32(np.int64(sum(partials)).astype(np.int32))
+    fvals = rng.uniform(-100, 100, n).astype(np.float32)
+    fa = ag.Float32ArrayGPU.from_numpy(fvals[b:e], None, dev)
+    import oracle as O
+    fparts = [O.sum(O.F32, fvals[slice(*sharded.row_range(n, r, world))]) for r in range(world)]
+    got_f = sharded.sharded_sum(fa)
+    assert got_f == sharded.combine_partial_sums(np.array(fparts, dtype=np.float32), np.float32), (got_f, fparts)
+    flags = np.zeros(n, dtype=bool)
+    flags[n - 5] = True                                  # a single set bit, in the last shard
+    fl = ag.BooleanArrayGPU.from_numpy(flags[b:e], None, dev)
+    assert sharded.sharded_any(fl) is True and sharded.sharded_all(fl) is False
+    assert sharded.sharded_any(fl.bitwise_and(fl.bitwise_not())) is False
+    assert sharded.sharded_all(fl.bitwise_or(fl.bitwise_not())) is True
+
     # global-index take over peer memory (CUDA IPC + NVLink loads inside the gather kernel)
     col = sharded.ShardedColumn(ag.Int32ArrayGPU, vals[b:e], valid[b:e], n, dev)
     gidx = np.random.default_rng(1000 + rank).integers(0, n, 200_003).astype(np.uint32)

@@ -86,7 +86,8 @@ def _gloo_worker(rank, world, port, q):
         local = [7, 11][rank]
         offsets, total = sharded.exchange_counts(local)
         mx = sharded.max_over_ranks(float(rank + 1))
-        q.put((rank, offsets, total, mx))
+        words = sharded.gather_words([0x3F800000, 0xFFFFFFFF][rank])
+        q.put((rank, offsets, total, mx, words))
     finally:
         dist.destroy_process_group()
 
@@ -104,5 +105,15 @@ def test_count_exchange_two_ranks_gloo():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    assert res[0] == (0, [0, 7], 18, 2.0)
-    assert res[1] == (1, [0, 7], 18, 2.0)
+    assert res[0] == (0, [0, 7], 18, 2.0, [0x3F800000, 0xFFFFFFFF])
+    assert res[1] == (1, [0, 7], 18, 2.0, [0x3F800000, 0xFFFFFFFF])
+
+
+def test_combine_partial_sums_is_a_rank_ordered_fold():
+    """the cross-shard sum is defined, not left to the collective: f32 adds in rank order, ints wrap"""
+    f = sharded.combine_partial_sums(np.array([1e8, 1.0, -1e8, 1.0], dtype=np.float32), np.float32)
+    assert f == np.float32(np.float32(np.float32(np.float32(1e8) + np.float32(1.0)) - np.float32(1e8)) + np.float32(1.0))
+    assert f == np.float32(1.0)               # (1e8 + 1) rounds to 1e8 in f32: order matters and is fixed
+    assert sharded.combine_partial_sums(np.array([2**31 - 1, 1], dtype=np.int32), np.int32) == np.int32(-2**31)
+    assert sharded.combine_partial_sums(np.array([2**32 - 1, 2], dtype=np.uint32), np.uint32) == np.uint32(1)
+    assert sharded.combine_partial_sums(np.array([], dtype=np.float32), np.float32) == np.float32(0)
