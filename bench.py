@@ -359,6 +359,9 @@ def cpu_runner():
 
 def time_cpu(sample_rows: int, steps: int, warmup: int, cols=None):
     O, run = cpu_runner()
+    # all host threads this process may use — torchrun exports OMP_NUM_THREADS=1 to its workers,
+    # which would otherwise time the CPU arm on a single core
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     ops = cfg2_ops()
     if cols is None:
         cols = cfg2_columns(sample_rows)
