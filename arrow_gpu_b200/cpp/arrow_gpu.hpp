@@ -538,6 +538,57 @@ inline ArrowArrayGPU cast_dyn(const ArrowArrayGPU& from, ArrowType into) {
   }, from);
 }
 
+// bitcast_dyn (cast/src/lib.rs:187-192): only u32 -> f32 exists
+inline ArrowArrayGPU bitcast_dyn(const ArrowArrayGPU& from, ArrowType into) {
+  if (auto u = std::get_if<UInt32ArrayGPU>(&from); u && into == ArrowType::Float32Type) return u->bitcast<Float32ArrayGPU>();
+  throw Panic("Casting not supported");
+}
+// put_dyn (routines/src/put.rs:59-108): same-typed 32-bit columns
+inline void put_dyn(const ArrowArrayGPU& src, const UInt32ArrayGPU& src_indexes, ArrowArrayGPU& dst, const UInt32ArrayGPU& dst_indexes) {
+  std::visit([&](const auto& x) {
+    using A = std::decay_t<decltype(x)>;
+    if constexpr (detail::is_bool<A>) {
+      throw Panic("Put Operation on BooleanType: use the C ABI (agpu_put with AGPU_BOOL)");
+    } else if constexpr (sizeof(typename A::Native) != 4) {
+      throw Panic("Put Operation not supported for this type");
+    } else {
+      if (auto y = std::get_if<A>(&dst)) x.put(src_indexes, *y, dst_indexes);
+      else throw Panic("Put Operation not supported for this type pair");
+    }
+  }, src);
+}
+// broadcast_dyn (array/mod.rs:189-200): ScalarValue::F32(x) ... -> the variant alternative
+using ScalarValue = std::variant<float, uint32_t, uint16_t, uint8_t, int32_t, int16_t, int8_t, bool>;
+inline ArrowArrayGPU broadcast_dyn(const ScalarValue& value, size_t len, const DevicePtr& device) {
+  return std::visit([&](auto v) -> ArrowArrayGPU {
+    using V = decltype(v);
+    if constexpr (std::is_same<V, bool>::value) return BooleanArrayGPU::from_slice(std::vector<bool>(len, v), device);
+    else return PrimitiveArrayGpu<V>::broadcast(v, len, device);
+  }, value);
+}
+
+// the recording forms (`*_op_dyn`, pipeline last): a pipeline is a stream scope here, so they
+// enqueue exactly what the eager forms enqueue
+#define AGPU_OP_DYN1(n) inline ArrowArrayGPU n##_op_dyn(const ArrowArrayGPU& a, ArrowComputePipeline&) { return n##_dyn(a); }
+#define AGPU_OP_DYN2(n) \
+  inline ArrowArrayGPU n##_op_dyn(const ArrowArrayGPU& a, const ArrowArrayGPU& b, ArrowComputePipeline&) { return n##_dyn(a, b); }
+AGPU_OP_DYN1(neg) AGPU_OP_DYN1(abs) AGPU_OP_DYN1(sqrt) AGPU_OP_DYN1(cbrt) AGPU_OP_DYN1(exp) AGPU_OP_DYN1(exp2) AGPU_OP_DYN1(log)
+AGPU_OP_DYN1(log2) AGPU_OP_DYN1(sin) AGPU_OP_DYN1(cos) AGPU_OP_DYN1(acos) AGPU_OP_DYN1(sinh) AGPU_OP_DYN1(bitwise_not)
+AGPU_OP_DYN2(add) AGPU_OP_DYN2(sub) AGPU_OP_DYN2(mul) AGPU_OP_DYN2(div)
+AGPU_OP_DYN2(add_array) AGPU_OP_DYN2(sub_array) AGPU_OP_DYN2(mul_array) AGPU_OP_DYN2(div_array)
+AGPU_OP_DYN2(add_scalar) AGPU_OP_DYN2(sub_scalar) AGPU_OP_DYN2(mul_scalar) AGPU_OP_DYN2(div_scalar) AGPU_OP_DYN2(rem_scalar)
+AGPU_OP_DYN2(min) AGPU_OP_DYN2(max) AGPU_OP_DYN2(power)
+AGPU_OP_DYN2(gt) AGPU_OP_DYN2(gteq) AGPU_OP_DYN2(lt) AGPU_OP_DYN2(lteq) AGPU_OP_DYN2(eq)
+AGPU_OP_DYN2(bitwise_and) AGPU_OP_DYN2(bitwise_or) AGPU_OP_DYN2(bitwise_xor) AGPU_OP_DYN2(bitwise_shl) AGPU_OP_DYN2(bitwise_shr)
+#undef AGPU_OP_DYN1
+#undef AGPU_OP_DYN2
+inline ArrowArrayGPU merge_op_dyn(const ArrowArrayGPU& a, const ArrowArrayGPU& b, const BooleanArrayGPU& mask, ArrowComputePipeline&) { return merge_dyn(a, b, mask); }
+inline ArrowArrayGPU take_op_dyn(const ArrowArrayGPU& a, const UInt32ArrayGPU& idx, ArrowComputePipeline&) { return take_dyn(a, idx); }
+inline ArrowArrayGPU cast_op_dyn(const ArrowArrayGPU& from, ArrowType into, ArrowComputePipeline&) { return cast_dyn(from, into); }
+inline ArrowArrayGPU bitcast_op_dyn(const ArrowArrayGPU& from, ArrowType into, ArrowComputePipeline&) { return bitcast_dyn(from, into); }
+inline void put_op_dyn(const ArrowArrayGPU& src, const UInt32ArrayGPU& si, ArrowArrayGPU& dst, const UInt32ArrayGPU& di, ArrowComputePipeline&) { put_dyn(src, si, dst, di); }
+inline ArrowArrayGPU broadcast_op_dyn(const ScalarValue& value, size_t len, ArrowComputePipeline& pipeline) { return broadcast_dyn(value, len, pipeline.device); }
+
 // fused expression of BASELINE.json config 3: ((a*b)+c) > d, bit-identical to the unfused chain
 inline BooleanArrayGPU fused_mul_add_gt(const Float32ArrayGPU& a, const Float32ArrayGPU& b, const Float32ArrayGPU& c,
                                         const Float32ArrayGPU& d) {

@@ -148,6 +148,28 @@ int main() {
     CHECK(std::get<BooleanArrayGPU>(chained).raw_values() == ga.mul(gb).add(gc).gt(gd).raw_values());
     auto chain_vals = fused_chain(Int8ArrayGPU::from_slice({0, 1, 4, 9, -16}, device), {ChainStep::unary(AGPU_ABS), ChainStep::unary(AGPU_SQRT), ChainStep::binary(AGPU_MUL, 2.0f)});
     CHECK(feq(std::get<Float32ArrayGPU>(chain_vals).raw_values(), {0, 2, 4, 6, 8}));
+    // dyn layer incl. the recording forms, broadcast, bitcast and put
+    {
+      ArrowComputePipeline pipe(device, "dyn");
+      ArrowArrayGPU x = Int32ArrayGPU::from_slice({1, -2, 3}, device), y = Int32ArrayGPU::from_slice({10, 20, 30}, device);
+      auto sum = add_op_dyn(x, y, pipe);
+      auto m = gt_op_dyn(sum, y, pipe);
+      pipe.finish();
+      CHECK((std::get<Int32ArrayGPU>(sum).raw_values() == std::vector<int32_t>{11, 18, 33}));
+      CHECK((std::get<BooleanArrayGPU>(m).raw_values() == std::vector<bool>{true, false, true}));
+      auto bc = broadcast_dyn(ScalarValue{uint16_t(7)}, 5, device);
+      CHECK((std::get<UInt16ArrayGPU>(bc).raw_values() == std::vector<uint16_t>(5, 7)));
+      auto bb = broadcast_dyn(ScalarValue{true}, 35, device);
+      CHECK(std::get<BooleanArrayGPU>(bb).all());
+      ArrowArrayGPU bits = UInt32ArrayGPU::from_slice({0x3F800000u, 0xC0000000u}, device);
+      CHECK(feq(std::get<Float32ArrayGPU>(bitcast_dyn(bits, ArrowType::Float32Type)).raw_values(), {1.0f, -2.0f}));
+      ArrowArrayGPU dst = Int32ArrayGPU::from_slice({0, 0, 0, 0}, device);
+      put_dyn(x, UInt32ArrayGPU::from_slice({0, 2}, device), dst, UInt32ArrayGPU::from_slice({3, 1}, device));
+      CHECK((std::get<Int32ArrayGPU>(dst).raw_values() == std::vector<int32_t>{0, 3, 0, 1}));
+      bool threw = false;
+      try { bitcast_dyn(x, ArrowType::Float32Type); } catch (const Panic&) { threw = true; }
+      CHECK(threw);
+    }
     // integer chain: ((x + y) & 0x0F) * 3 with u8 wrap, then > y  — one kernel each
     auto ux = UInt8ArrayGPU::from_slice({250, 7, 16, 255, 0}, device);
     auto uy = UInt8ArrayGPU::from_slice({10, 9, 16, 1, 0}, device);
