@@ -276,6 +276,13 @@ extern "C" int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, 
     }
   }
   if (vout && !vals[0] && !vals[1] && !vals[2] && !vals[3]) return AGPU_EINVAL;
+  // the config-3 expression ((a*b)+c) > d has a dedicated kernel with the same roundings
+  // (compare.cu): a recorded mul -> add -> gt chain over three columns is routed to it
+  if (in_dtype == AGPU_F32 && n_steps == 3 && steps[0].kind == AGPU_STEP_BINARY_COLUMN && steps[0].op == AGPU_MUL &&
+      steps[1].kind == AGPU_STEP_BINARY_COLUMN && steps[1].op == AGPU_ADD && steps[2].kind == AGPU_STEP_COMPARE_COLUMN &&
+      steps[2].op == AGPU_GT)
+    return agpu_fused_mul_add_gt(dev, (const float*)in, p.cols[0], p.cols[1], p.cols[2], (uint32_t*)out, n, vals[0], vals[1],
+                                 vals[2], vals[3], vout);
   const BmAnd bm = make_bm(vals[0], vals[1], vals[2], vals[3], vout);
   switch (in_dtype) {
     case AGPU_F32: return run_chain<float>(dev, p, in, out, n, bm, is_pred);
