@@ -57,6 +57,15 @@ def main():
         ag.Int32ArrayGPU.from_numpy(i32, None, dev).put(ag.UInt32ArrayGPU.from_numpy(idx, None, dev), dst,
                                                         ag.UInt32ArrayGPU.from_numpy(rng.permutation(n).astype(np.uint32), None, dev))
         m.any(), m.all(), m.bitwise_not(), m.take(ag.UInt32ArrayGPU.from_numpy(idx, None, dev))
+        # fused chains: f32 interpreter, integer packed-word interpreter (value + predicate), u16 filter
+        K.fused_chain(fa, [("abs",), ("sqrt",), ("mul", fa), ("lteq", fa)])
+        s8 = ag.Int8ArrayGPU.from_slice([3], dev)
+        got = K.fused_chain_int(a, [("add", b), ("bitwise_and", b), ("mul", K.DeviceScalar(s8))])
+        assert np.array_equal(got.raw_values(), a.add(b).bitwise_and(b).mul_scalar(s8).raw_values())
+        got = K.fused_chain_int(ia, [("bitwise_not",), ("div", ia), ("gt", ia)])
+        assert np.array_equal(got.raw_values(), ia.bitwise_not().div(ia).gt(ia).raw_values())
+        u16 = rng.integers(0, 65536, n).astype(np.uint16)
+        assert np.array_equal(ag.UInt16ArrayGPU.from_numpy(u16, None, dev).filter(m).raw_values(), u16[flags & vb])
     dev.sync()
     print("sanitizer smoke ok,", dev.launch_count(), "launches")
 
