@@ -26,11 +26,22 @@ struct ChainProgram {
   const float* cols[kMaxCols];
 };
 
-template <int N>
+// HEAVY = the chain contains a transcendental / pow step.  The arithmetic-only interpreter
+// (neg abs sqrt, + - * / % min max, compares) is a separate, much smaller kernel: the register
+// allocation of the full one is set by powf / the sinf slow path whatever the chain executes.
+template <int N, bool HEAVY>
 __device__ __forceinline__ void apply_unary(int op, float (&a)[N]) {
 #define U4(F)                          \
   _Pragma("unroll") for (int k = 0; k < N; ++k) a[k] = F<float>{}(a[k]); \
   break;
+  if constexpr (!HEAVY) {
+    switch (op) {
+      case AGPU_NEG: U4(OpNeg)
+      case AGPU_ABS: U4(OpAbs)
+      default: U4(FSqrt)
+    }
+    return;
+  }
   switch (op) {
     case AGPU_NEG: U4(OpNeg)
     case AGPU_ABS: U4(OpAbs)
@@ -49,11 +60,23 @@ __device__ __forceinline__ void apply_unary(int op, float (&a)[N]) {
 #undef U4
 }
 
-template <int N>
+template <int N, bool HEAVY>
 __device__ __forceinline__ void apply_binary(int op, float (&a)[N], const float (&b)[N]) {
 #define B4(F)                          \
   _Pragma("unroll") for (int k = 0; k < N; ++k) a[k] = F<float>{}(a[k], b[k]); \
   break;
+  if constexpr (!HEAVY) {
+    switch (op) {
+      case AGPU_ADD: B4(OpAdd)
+      case AGPU_SUB: B4(OpSub)
+      case AGPU_MUL: B4(OpMul)
+      case AGPU_DIV: B4(OpDiv)
+      case AGPU_REM: B4(OpRem)
+      case AGPU_MIN: B4(OpMin)
+      default: B4(OpMax)
+    }
+    return;
+  }
   switch (op) {
     case AGPU_ADD: B4(OpAdd)
     case AGPU_SUB: B4(OpSub)
@@ -86,19 +109,22 @@ __device__ __forceinline__ uint32_t apply_compare(int op, const float (&a)[N], c
   return m;
 }
 
-template <typename TI>
+// NC = operand-column slots held in registers (8 registers per slot with two granules in
+// flight); the arithmetic-only kernels are specialised on the exact column count
+template <typename TI, int NC, bool HEAVY>
 struct ChainOp {
   static constexpr int G = 4;
+  static constexpr int NCA = NC ? NC : 1;
   ChainProgram p;
   const TI* in;
   float* out;  // value chains only
-  struct In { Vec<TI, 4> a; Vec<float, 4> c[kMaxCols]; };
+  struct In { Vec<TI, 4> a; Vec<float, 4> c[NCA]; };
 
   __device__ __forceinline__ In load(size_t g) const {
     In r;
     r.a = ld_vec<TI, 4>(in, g);
 #pragma unroll
-    for (int k = 0; k < kMaxCols; ++k)
+    for (int k = 0; k < NC; ++k)
       if (k < p.n_cols) r.c[k] = ld_vec<float, 4>(p.cols[k], g);
     return r;
   }
@@ -120,7 +146,7 @@ struct ChainOp {
     for (int s = 0; s < p.n_steps; ++s) {
       const int kind = p.kind[s];
       if (kind == AGPU_STEP_UNARY) {
-        apply_unary<4 * U>(p.op[s], acc);
+        apply_unary<4 * U, HEAVY>(p.op[s], acc);
       } else {
         if (kind == AGPU_STEP_BINARY_SCALAR || kind == AGPU_STEP_COMPARE_SCALAR) {
 #pragma unroll
@@ -129,16 +155,20 @@ struct ChainOp {
           const float v = __ldg(p.dscalar[s]);
 #pragma unroll
           for (int k = 0; k < 4 * U; ++k) rhs[k] = v;
-        } else {
-          const int c = p.col[s];
+        } else if constexpr (NC > 0) {
+          const int c = p.col[s];  // warp-uniform select between the statically named column chunks
 #pragma unroll
           for (int j = 0; j < U; ++j)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              rhs[j * 4 + k] = c == 0 ? in4[j].c[0].e[k] : (c == 1 ? in4[j].c[1].e[k] : in4[j].c[2].e[k]);
+            for (int k = 0; k < 4; ++k) {
+              float v = in4[j].c[0].e[k];
+              if constexpr (NC > 1) v = c == 1 ? in4[j].c[1].e[k] : v;
+              if constexpr (NC > 2) v = c == 2 ? in4[j].c[2].e[k] : v;
+              rhs[j * 4 + k] = v;
+            }
         }
         if (kind == AGPU_STEP_BINARY_COLUMN || kind == AGPU_STEP_BINARY_SCALAR || kind == AGPU_STEP_BINARY_DEVSCALAR)
-          apply_binary<4 * U>(p.op[s], acc, rhs);
+          apply_binary<4 * U, HEAVY>(p.op[s], acc, rhs);
         else cmp_op = p.op[s];  // compare is the last step (checked on the host)
       }
     }
@@ -175,7 +205,7 @@ struct ChainOp {
 #pragma unroll
     for (int k = 1; k < 4; ++k) r.a.e[k] = r.a.e[0];
 #pragma unroll
-    for (int c = 0; c < kMaxCols; ++c)
+    for (int c = 0; c < NC; ++c)
       if (c < p.n_cols) {
         const float v = p.cols[c][i];
 #pragma unroll
@@ -214,16 +244,32 @@ struct ChainOp {
   }
 };
 
-template <typename TI>
-int run_chain(agpu_device* dev, const ChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm, bool is_pred) {
-  ChainOp<TI> op{p, (const TI*)in, (float*)out};
+template <typename TI, int NC, bool HEAVY>
+int run_chain_as(agpu_device* dev, const ChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm, bool is_pred) {
+  using Op = ChainOp<TI, NC, HEAVY>;
+  Op op{p, (const TI*)in, (float*)out};
   bool al = aligned16(in) && aligned16(out);
   for (int k = 0; k < p.n_cols; ++k) al = al && aligned16(p.cols[k]);
-  // two granules per thread evaluated jointly: 64 registers, 0.80-0.93 of peak; four (126
-  // registers) measured 30 % slower.  Specialising on the number of operand columns (as
-  // chain_int.cu does, where it lifts 0.70 to 0.93-1.09) measured no gain here (-1 % .. +3 %).
-  if (is_pred) return launch_bits<ChainOp<TI>, 2>(dev, op, (uint32_t*)out, n, bm, al);
-  return launch_ew<ChainOp<TI>, 2>(dev, op, n, bm, al);
+  // two granules per thread evaluated jointly; four (126 registers in the full interpreter)
+  // measured 30 % slower
+  if (is_pred) return launch_bits<Op, 2>(dev, op, (uint32_t*)out, n, bm, al);
+  return launch_ew<Op, 2>(dev, op, n, bm, al);
+}
+
+template <typename TI>
+int run_chain(agpu_device* dev, const ChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm, bool is_pred,
+              bool heavy) {
+  if constexpr (std::is_same<TI, float>::value) {
+    if (!heavy) {
+      switch (p.n_cols) {
+        case 0: return run_chain_as<TI, 0, false>(dev, p, in, out, n, bm, is_pred);
+        case 1: return run_chain_as<TI, 1, false>(dev, p, in, out, n, bm, is_pred);
+        case 2: return run_chain_as<TI, 2, false>(dev, p, in, out, n, bm, is_pred);
+        default: return run_chain_as<TI, 3, false>(dev, p, in, out, n, bm, is_pred);
+      }
+    }
+  }
+  return run_chain_as<TI, kMaxCols, true>(dev, p, in, out, n, bm, is_pred);
 }
 
 }  // namespace
@@ -236,9 +282,12 @@ extern "C" int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, 
   ChainProgram p{};
   p.n_steps = n_steps;
   const uint32_t* vals[4] = {vin, nullptr, nullptr, nullptr};
-  bool is_pred = false;
+  bool is_pred = false, heavy = false;
   for (int s = 0; s < n_steps; ++s) {
     const agpu_chain_step& st = steps[s];
+    if (st.kind == AGPU_STEP_UNARY) heavy = heavy || (st.op != AGPU_NEG && st.op != AGPU_ABS && st.op != AGPU_SQRT);
+    else if (st.kind == AGPU_STEP_BINARY_COLUMN || st.kind == AGPU_STEP_BINARY_SCALAR || st.kind == AGPU_STEP_BINARY_DEVSCALAR)
+      heavy = heavy || st.op == AGPU_POW;
     p.kind[s] = st.kind;
     p.op[s] = st.op;
     p.scalar[s] = st.scalar;
@@ -285,11 +334,11 @@ extern "C" int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, 
                                  vals[2], vals[3], vout);
   const BmAnd bm = make_bm(vals[0], vals[1], vals[2], vals[3], vout);
   switch (in_dtype) {
-    case AGPU_F32: return run_chain<float>(dev, p, in, out, n, bm, is_pred);
-    case AGPU_I8: return run_chain<int8_t>(dev, p, in, out, n, bm, is_pred);
-    case AGPU_U8: return run_chain<uint8_t>(dev, p, in, out, n, bm, is_pred);
-    case AGPU_I16: return run_chain<int16_t>(dev, p, in, out, n, bm, is_pred);
-    case AGPU_U16: return run_chain<uint16_t>(dev, p, in, out, n, bm, is_pred);
+    case AGPU_F32: return run_chain<float>(dev, p, in, out, n, bm, is_pred, heavy);
+    case AGPU_I8: return run_chain<int8_t>(dev, p, in, out, n, bm, is_pred, heavy);
+    case AGPU_U8: return run_chain<uint8_t>(dev, p, in, out, n, bm, is_pred, heavy);
+    case AGPU_I16: return run_chain<int16_t>(dev, p, in, out, n, bm, is_pred, heavy);
+    case AGPU_U16: return run_chain<uint16_t>(dev, p, in, out, n, bm, is_pred, heavy);
     default: return AGPU_EUNSUPPORTED;
   }
 }

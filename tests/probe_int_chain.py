@@ -52,3 +52,19 @@ for name, cls, tdt, es in (("i8", ag.Int8ArrayGPU, torch.int8, 1), ("u16", ag.UI
         print(f"{name:4s} [{label:22s}] fused {tf:.4f} ms ({bpr * n / tf / 1e6:7.1f} GB/s, frac {bpr * n / tf / 1e6 / PEAK:.3f})"
               f"   unfused {tu:.4f} ms   speed-up {tu / tf:.2f}x")
     del keep, a, b, c
+
+# f32 arithmetic-only chains (the light interpreter, specialised on the column count)
+tf32 = [torch.empty(n, dtype=torch.float32, device="cuda").uniform_(-5, 5, generator=g) for _ in range(3)]
+fa, fb, fc = (ag.Float32ArrayGPU(ag.ArrowGpuBuffer(dev, t.data_ptr(), n * 4, owned=False), dev, n, None) for t in tf32)
+sf = ag.Float32ArrayGPU.from_slice([1.5], dev)
+for label, steps, unfused, bpr in (
+        ("mul s, add s, abs", [("mul", K.DeviceScalar(sf)), ("add", K.DeviceScalar(sf)), ("abs",)],
+         lambda: fa.mul_scalar(sf).add_scalar(sf).abs(), 8),
+        ("mul b, add s, sqrt", [("mul", fb), ("add", K.DeviceScalar(sf)), ("sqrt",)],
+         lambda: fa.mul(fb).add_scalar(sf).sqrt(), 12),
+        ("mul b, add c, max s", [("mul", fb), ("add", fc), ("max", 2.0)], None, 16),
+        ("sin, mul b, add c (heavy)", [("sin",), ("mul", fb), ("add", fc)], lambda: fa.sin().mul(fb).add(fc), 16)):
+    tf = timeit(lambda: K.fused_chain(fa, steps))
+    tu = timeit(unfused) if unfused else float("nan")
+    print(f"f32  [{label:26s}] fused {tf:.4f} ms ({bpr * n / tf / 1e6:7.1f} GB/s, frac {bpr * n / tf / 1e6 / PEAK:.3f})"
+          f"   unfused {tu:.4f} ms   speed-up {tu / tf:.2f}x")
