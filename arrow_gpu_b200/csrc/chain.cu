@@ -259,14 +259,17 @@ int run_chain_as(agpu_device* dev, const ChainProgram& p, const void* in, void* 
 template <typename TI>
 int run_chain(agpu_device* dev, const ChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm, bool is_pred,
               bool heavy) {
-  if constexpr (std::is_same<TI, float>::value) {
-    if (!heavy) {
+  if (!heavy) {
+    if constexpr (std::is_same<TI, float>::value) {
       switch (p.n_cols) {
         case 0: return run_chain_as<TI, 0, false>(dev, p, in, out, n, bm, is_pred);
         case 1: return run_chain_as<TI, 1, false>(dev, p, in, out, n, bm, is_pred);
         case 2: return run_chain_as<TI, 2, false>(dev, p, in, out, n, bm, is_pred);
         default: return run_chain_as<TI, 3, false>(dev, p, in, out, n, bm, is_pred);
       }
+    } else {  // fused int -> f32 cast + arithmetic (e.g. u8 * scale + offset): two variants
+      if (p.n_cols == 0) return run_chain_as<TI, 0, false>(dev, p, in, out, n, bm, is_pred);
+      return run_chain_as<TI, kMaxCols, false>(dev, p, in, out, n, bm, is_pred);
     }
   }
   return run_chain_as<TI, kMaxCols, true>(dev, p, in, out, n, bm, is_pred);

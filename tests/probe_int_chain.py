@@ -68,3 +68,11 @@ for label, steps, unfused, bpr in (
     tu = timeit(unfused) if unfused else float("nan")
     print(f"f32  [{label:26s}] fused {tf:.4f} ms ({bpr * n / tf / 1e6:7.1f} GB/s, frac {bpr * n / tf / 1e6 / PEAK:.3f})"
           f"   unfused {tu:.4f} ms   speed-up {tu / tf:.2f}x")
+
+# fused cast + arithmetic: u8 -> f32, * scale, + offset (5 B/row) vs cast, mul_scalar, add_scalar
+tu8 = torch.randint(0, 256, (n,), dtype=torch.int32, device="cuda", generator=g).to(torch.uint8)
+u8 = ag.UInt8ArrayGPU(ag.ArrowGpuBuffer(dev, tu8.data_ptr(), n, owned=False), dev, n, None)
+tf = timeit(lambda: K.fused_chain(u8, [("mul", K.DeviceScalar(sf)), ("add", K.DeviceScalar(sf))]))
+tu = timeit(lambda: u8.cast(ag.Float32ArrayGPU).mul_scalar(sf).add_scalar(sf))
+print(f"u8   [cast f32, mul s, add s      ] fused {tf:.4f} ms ({5 * n / tf / 1e6:7.1f} GB/s, frac {5 * n / tf / 1e6 / PEAK:.3f})"
+      f"   unfused {tu:.4f} ms   speed-up {tu / tf:.2f}x")
