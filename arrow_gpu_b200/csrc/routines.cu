@@ -249,12 +249,26 @@ int run_take_sharded(agpu_device* dev, const ShardTable& t, const uint32_t* idx,
 // ============================================================================================
 // put: routines/compute_shaders/32bit/put.wgsl:17-23, bool/put.wgsl:17-34
 // ============================================================================================
+// granule = 4 (source index, destination index) pairs: two 16-byte index chunks per lane, all
+// index chunks of the tile in flight first, then 4 gathers and 4 scattered stores per granule
 template <typename U>
-__global__ void __launch_bounds__(kBlock) put_kernel(const U* __restrict__ src, const uint32_t* __restrict__ si,
-                                                     U* dst, const uint32_t* __restrict__ di, const size_t m) {
-  const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i < m) dst[di[i]] = src[si[i]];
-}
+struct PutOp {
+  static constexpr int G = 4;
+  const U* src;
+  const uint32_t* si;
+  U* dst;
+  const uint32_t* di;
+  struct In { Vec<uint32_t, 4> s, d; };
+  __device__ __forceinline__ In load(size_t g) const { return In{ld_vec<uint32_t, 4>(si, g), ld_vec<uint32_t, 4>(di, g)}; }
+  __device__ __forceinline__ void run(size_t, const In& in) const {
+    U v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = src[in.s.e[k]];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[in.d.e[k]] = v[k];
+  }
+  __device__ __forceinline__ void tail(size_t j) const { dst[di[j]] = src[si[j]]; }
+};
 
 __global__ void __launch_bounds__(kBlock) put_bits_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ si,
                                                           uint32_t* dst, const uint32_t* __restrict__ di, const size_t m) {
@@ -899,13 +913,14 @@ extern "C" int agpu_put(agpu_device* dev, int dtype, const void* src, const uint
     AGPU_LAUNCH(dev, put_bits_kernel, grid, kBlock, 0, (const uint32_t*)src, src_idx, (uint32_t*)dst, dst_idx, m);
     return agpu_finish_launch();
   }
+  BmAnd none{};
+  const bool al = aligned16(src_idx) && aligned16(dst_idx);
   switch (agpu_dtype_size(dtype)) {
-    case 4: AGPU_LAUNCH(dev, put_kernel<uint32_t>, grid, kBlock, 0, (const uint32_t*)src, src_idx, (uint32_t*)dst, dst_idx, m); break;
-    case 2: AGPU_LAUNCH(dev, put_kernel<uint16_t>, grid, kBlock, 0, (const uint16_t*)src, src_idx, (uint16_t*)dst, dst_idx, m); break;
-    case 1: AGPU_LAUNCH(dev, put_kernel<uint8_t>, grid, kBlock, 0, (const uint8_t*)src, src_idx, (uint8_t*)dst, dst_idx, m); break;
+    case 4: return launch_ew(dev, PutOp<uint32_t>{(const uint32_t*)src, src_idx, (uint32_t*)dst, dst_idx}, m, none, al);
+    case 2: return launch_ew(dev, PutOp<uint16_t>{(const uint16_t*)src, src_idx, (uint16_t*)dst, dst_idx}, m, none, al);
+    case 1: return launch_ew(dev, PutOp<uint8_t>{(const uint8_t*)src, src_idx, (uint8_t*)dst, dst_idx}, m, none, al);
     default: return AGPU_EUNSUPPORTED;
   }
-  return agpu_finish_launch();
 }
 
 extern "C" size_t agpu_filter_scratch_bytes(size_t n) {

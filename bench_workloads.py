@@ -235,6 +235,18 @@ def run(args, rank, world, local_rank, helpers):
             ("i8.filter s=0.5", 1.125 + 0.5, n, lambda: i8a.filter(m)), ("u16.filter s=0.5", 2.125 + 1, n, lambda: u16a.filter(m)),
             ("f32.filter s=0.5 (+validity)", 4.25 + 2.0625, n, lambda: f[0].filter(m)),
         ]
+        # gathers / scatters outside config 5: sequential indices (the streaming bound of the kernel)
+        seq = torch.arange(n, dtype=torch.int32, device=tdev)
+        keep.append(seq)
+        idx = ag.UInt32ArrayGPU(ag.ArrowGpuBuffer(dev, seq.data_ptr(), n * 4, owned=False), dev, n, None)
+        dst = ag.Int32ArrayGPU.empty(n, dev)
+        ops += [
+            ("f32.take sequential (+validity gather)", 12.25, n, lambda: f[0].take(idx)),
+            ("i8.take sequential", 6, n, lambda: i8a.take(idx)),
+            ("bool.take sequential", 4.25, n, lambda: m.take(idx)),
+            ("i32.put sequential (one index column used for both sides)", 12, n, lambda: i32[0].put(idx, dst, idx)),
+            ("f32.broadcast", 4, n, lambda: ag.Float32ArrayGPU.broadcast(1.5, n, dev)),
+        ]
         # fused integer chains (agpu_fused_chain_int) and the same ops one kernel each
         from arrow_gpu_b200 import kernels as K
         sc8 = ag.Int8ArrayGPU.from_slice([3], dev)
