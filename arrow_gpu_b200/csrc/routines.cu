@@ -434,11 +434,32 @@ __device__ __forceinline__ void stage_if(uint32_t& sa, U val, uint32_t bit) {
   }
 }
 
+// sub-word rows: the lane stays inside its packed 32-bit word until the predicated store (taking
+// the lanes out up front costs 64 live registers for a 1-byte tile and spills)
+template <int BYTES, int SHIFT>
+__device__ __forceinline__ void stage_lane_if(uint32_t& sa, uint32_t word, uint32_t bit) {
+  if constexpr (BYTES == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tsetp.ne.u32 p, %2, 0;\n\tshr.u32 t, %1, %3;\n\t@p st.shared.u8 [%0], t;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                 : "+r"(sa) : "r"(word), "r"(bit), "n"(SHIFT) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tsetp.ne.u32 p, %2, 0;\n\tshr.u32 t, %1, %3;\n\t@p st.shared.u16 [%0], t;\n\t@p add.u32 %0, %0, 2;\n\t}"
+                 : "+r"(sa) : "r"(word), "r"(bit), "n"(SHIFT) : "memory");
+  }
+}
+template <typename U, int K>
+__device__ __forceinline__ void stage_lanes(uint32_t& sa, const uint32_t (&w)[4], uint32_t bits) {
+  constexpr int L = 4 / sizeof(U);  // lanes per word
+  if constexpr (K < 16 / (int)sizeof(U)) {
+    stage_lane_if<sizeof(U), (K % L) * 8 * (int)sizeof(U)>(sa, w[K / L], bits & (1u << K));
+    stage_lanes<U, K + 1>(sa, w, bits);
+  }
+}
+
 // One CTA compacts a "super tile" of M = 4/sizeof(U) count-tiles, i.e. always 16 KiB of rows
 // (4096 x 4-byte, 8192 x 2-byte or 16384 x 1-byte rows): the per-tile barriers and prefix sums are
 // amortised over the same number of bytes for every element width.
 template <typename U, bool HAS_V, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1024 : 2048) / BLOCK) filter_scatter_kernel(const U* __restrict__ src,
+__global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK) filter_scatter_kernel(const U* __restrict__ src,
                                                                 const uint32_t* __restrict__ vsrc,
                                                                 const uint32_t* __restrict__ mask,
                                                                 const uint32_t* __restrict__ vmask, const size_t n,
@@ -528,11 +549,21 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1024 : 2048) / BLOCK)
       // compiler's form of `pos += take` is a 3-instruction select-and-add per row)
       uint32_t sa = stage_sa + pos * (uint32_t)sizeof(U);
       uint32_t va = vbyte_sa + pos;
+      if constexpr (sizeof(U) < 4) {
+        uint32_t w[4];
+        memcpy(w, &v[j], 16);
+        stage_lanes<U, 0>(sa, w, bits);
+        if (HAS_V) {
 #pragma unroll
-      for (int k = 0; k < G; ++k) {
-        const uint32_t bit = bits & (1u << k);
-        stage_if<U>(sa, v[j].e[k], bit);
-        if (HAS_V) stage_if<uint8_t>(va, (uint8_t)((vw >> k) & 1u), bit);
+          for (int k = 0; k < G; ++k) stage_if<uint8_t>(va, (uint8_t)((vw >> k) & 1u), bits & (1u << k));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          const uint32_t bit = bits & (1u << k);
+          stage_if<U>(sa, v[j].e[k], bit);
+          if (HAS_V) stage_if<uint8_t>(va, (uint8_t)((vw >> k) & 1u), bit);
+        }
       }
     }
   } else {
