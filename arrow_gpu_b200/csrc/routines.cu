@@ -871,21 +871,15 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
     }
     return launch_filter_tma<U, false>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout);
   }
-  static const int block_env = getenv("AGPU_FILTER_BLOCK") ? atoi(getenv("AGPU_FILTER_BLOCK")) : 0;
-#define AGPU_FILTER_LAUNCH(HV, B)                                                                                   \
-  AGPU_LAUNCH(dev, (filter_scatter_kernel<U, HV, B>), (unsigned)super_tiles, B, 0, (const U*)src, vsrc, mask, vmask, n, \
-              sc.counts, sc.group_offsets, (U*)out, vout)
+  // 512- and 1024-thread CTAs measured 10-50 % slower (profiles/r01_filter_variants.md)
   if (vsrc && vout) {
     AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
-    if (block_env == 512) { AGPU_FILTER_LAUNCH(true, 512); }
-    else if (block_env == 1024) { AGPU_FILTER_LAUNCH(true, 1024); }
-    else { AGPU_FILTER_LAUNCH(true, BLOCK); }
+    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
+                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
   } else {
-    if (block_env == 512) { AGPU_FILTER_LAUNCH(false, 512); }
-    else if (block_env == 1024) { AGPU_FILTER_LAUNCH(false, 1024); }
-    else { AGPU_FILTER_LAUNCH(false, BLOCK); }
+    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
+                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
   }
-#undef AGPU_FILTER_LAUNCH
   return agpu_finish_launch();
 }
 
