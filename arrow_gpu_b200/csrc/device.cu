@@ -4,11 +4,18 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 extern "C" int agpu_abi_version(void) { return AGPU_ABI_VERSION; }
 
 static void release_cache(agpu_device* dev);
+
+// every live handle of this process: on an out-of-memory a handle asks the other handles of the
+// same GPU (e.g. an upload stream's handle) to give their cached blocks back as well
+static std::mutex g_registry_mu;
+static std::vector<agpu_device*> g_registry;
 
 extern "C" int agpu_device_count(int* out) {
   if (!out) return AGPU_EINVAL;
@@ -51,12 +58,21 @@ extern "C" int agpu_device_create(int ordinal, agpu_device** out) {
     const size_t v = (size_t)atoi(g);
     if (v) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, v);
   }
+  {
+    std::lock_guard<std::mutex> lock(g_registry_mu);
+    g_registry.push_back(d);
+  }
   *out = d;
   return 0;
 }
 
 extern "C" int agpu_device_destroy(agpu_device* dev) {
   if (!dev) return AGPU_EINVAL;
+  {
+    std::lock_guard<std::mutex> lock(g_registry_mu);
+    for (size_t k = 0; k < g_registry.size(); ++k)
+      if (g_registry[k] == dev) { g_registry.erase(g_registry.begin() + k); break; }
+  }
   cudaSetDevice(dev->ordinal);
   {
     std::lock_guard<std::mutex> lock(dev->mu);
@@ -115,10 +131,22 @@ extern "C" int agpu_alloc(agpu_device* dev, size_t bytes, void** out) {
   }
   AGPU_CUDA(cudaSetDevice(dev->ordinal));
   cudaError_t e = cudaMallocAsync(out, want, dev->stream);
-  if (e == cudaErrorMemoryAllocation) {  // give the cache back to the driver and retry once
+  if (e == cudaErrorMemoryAllocation) {  // give the caches back to the driver and retry once
     cudaGetLastError();
     release_cache(dev);
-    cudaStreamSynchronize(dev->stream);
+    {
+      // other handles of the same GPU: try_lock, so two handles running out of memory at the same
+      // moment cannot wait on each other
+      std::lock_guard<std::mutex> reg(g_registry_mu);
+      for (agpu_device* other : g_registry) {
+        if (other == dev || other->ordinal != dev->ordinal) continue;
+        if (other->mu.try_lock()) {
+          release_cache(other);
+          other->mu.unlock();
+        }
+      }
+    }
+    cudaDeviceSynchronize();  // the stream-ordered frees of every handle have to complete first
     e = cudaMallocAsync(out, want, dev->stream);
   }
   if (e != cudaSuccess) return (int)e;

@@ -163,3 +163,24 @@ def test_sharded_filter_nccl(device):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "multi-GPU check ok" in res.stdout
+
+
+def test_out_of_memory_releases_the_caches_of_every_handle(device):
+    """each handle keeps freed blocks; when one handle runs out of device memory the blocks cached
+    by the OTHER handles of the same GPU (an upload stream's handle, say) must be given back too"""
+    import torch
+    from arrow_gpu_b200 import _ffi
+    lib = _ffi.lib()
+    free_bytes, _total = torch.cuda.mem_get_info(device.ordinal)
+    big = int(free_bytes * 0.6) // (1 << 20) * (1 << 20)
+    other = ag.GpuDevice(device.ordinal)
+    blk = other.create_empty_buffer(big)
+    del blk                      # cached by `other`, not returned to the driver
+    other.sync()
+    got = device.create_empty_buffer(big)   # would not fit next to the cached block
+    assert got.size >= big
+    del got
+    lib.agpu_trim(device.handle)
+    lib.agpu_trim(other.handle)
+    device.sync()
+    other.sync()
