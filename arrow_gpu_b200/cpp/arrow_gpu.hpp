@@ -653,6 +653,16 @@ struct IntChainStep {
   static IntChainStep unary(agpu_unop op) { IntChainStep s; s.raw.kind = AGPU_STEP_UNARY; s.raw.op = op; return s; }
   static IntChainStep binary(agpu_binop op, const PrimitiveArrayGpu<T>& o, size_t len) { return with(op, o, len, AGPU_STEP_BINARY_COLUMN, AGPU_STEP_BINARY_DEVSCALAR); }
   static IntChainStep compare(agpu_cmpop op, const PrimitiveArrayGpu<T>& o, size_t len) { return with(op, o, len, AGPU_STEP_COMPARE_COLUMN, AGPU_STEP_COMPARE_DEVSCALAR); }
+  static IntChainStep shift(agpu_shiftop op, const UInt32ArrayGPU& counts, size_t len) {  // one per chain
+    if (counts.len != len) throw Panic("fused_chain_int: length mismatch");
+    IntChainStep s;
+    s.raw.kind = AGPU_STEP_SHIFT_COLUMN;
+    s.raw.op = op;
+    s.raw.operand = counts.data->ptr();
+    s.raw.validity = vptr(counts.null_buffer);
+    s.has_validity = bool(counts.null_buffer);
+    return s;
+  }
  private:
   static IntChainStep with(int op, const PrimitiveArrayGpu<T>& o, size_t len, int col_kind, int scalar_kind) {
     IntChainStep s;

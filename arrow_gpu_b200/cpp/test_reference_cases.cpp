@@ -178,6 +178,8 @@ int main() {
     using S8 = IntChainStep<uint8_t>;
     auto ichain = fused_chain_int(ux, {S8::binary(AGPU_ADD, uy, ux.len), S8::binary(AGPU_AND, u15, ux.len), S8::binary(AGPU_MUL, u3, ux.len)});
     CHECK((std::get<UInt8ArrayGPU>(ichain).raw_values() == std::vector<uint8_t>{12, 0, 0, 0, 0}));
+    auto ishift = fused_chain_int(ux, {S8::shift(AGPU_SHR, UInt32ArrayGPU::from_slice({1, 0, 4, 7, 33}, device), ux.len), S8::binary(AGPU_ADD, u3, ux.len)});
+    CHECK((std::get<UInt8ArrayGPU>(ishift).raw_values() == std::vector<uint8_t>{128, 10, 4, 4, 3}));
     auto ipred = fused_chain_int(ux, {S8::unary(AGPU_NOT), S8::compare(AGPU_GT, uy, ux.len)});
     CHECK((std::get<BooleanArrayGPU>(ipred).raw_values() == std::vector<bool>{false, true, true, false, true}));
     auto vals = Int32ArrayGPU::from_optional_slice({10, None, 30, 40, 50, 60}, device);

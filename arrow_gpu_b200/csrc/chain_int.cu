@@ -22,6 +22,7 @@ struct IntChainProgram {
   int op[AGPU_CHAIN_MAX_STEPS];
   const void* dscalar[AGPU_CHAIN_MAX_STEPS];  // one-element device arrays of the column type
   const void* cols[kMaxCols];
+  const uint32_t* counts;                     // the u32 per-row counts of the chain's shift step, or NULL
 };
 
 // ---- packed words: a 16-byte granule is four 32-bit words of L = 4/sizeof(T) lanes each --------
@@ -64,6 +65,22 @@ template <typename T> __device__ __forceinline__ uint32_t w_splat(T v) {  // the
   if constexpr (sizeof(T) == 1) return (uint32_t)(UT)v * 0x01010101u;
   else if constexpr (sizeof(T) == 2) return (uint32_t)(UT)v * 0x00010001u;
   else return (uint32_t)v;
+}
+
+// shift the L lanes of one word by their own counts (logical/compute_shaders/*/shift.wgsl: widen,
+// shift by count & 31, truncate) with the stand-alone functors
+template <typename T, bool LEFT>
+__device__ __forceinline__ uint32_t shift_lanes(uint32_t a, const uint32_t* c) {
+  constexpr int L = 4 / sizeof(T), B = 8 * sizeof(T);
+  using UT = typename std::make_unsigned<T>::type;
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const T x = (T)(UT)(a >> (B * k));
+    const T y = LEFT ? OpShl<T>{}(x, c[k]) : OpShr<T>{}(x, c[k]);
+    r |= (uint32_t)(UT)y << (B * k);
+  }
+  return r;
 }
 
 template <typename T, int N>
@@ -129,14 +146,16 @@ __device__ __forceinline__ uint32_t words_compare(int op, const uint32_t (&a)[N]
 
 // NC = number of operand columns of the chain: the granules of unused column slots would
 // otherwise still occupy registers (16 per slot with two granules in flight)
-template <typename T, int NC>
+// SH = the chain has a shift step: its u32 counts are G/4 more 16-byte chunks per granule
+template <typename T, int NC, bool SH>
 struct IntChainOp {
   static constexpr int G = 16 / sizeof(T);
   static constexpr int NCA = NC ? NC : 1;
+  static constexpr int CQ = SH ? G / 4 : 1;  // 16-byte chunks of counts per granule
   IntChainProgram p;
   const T* in;
   T* out;  // value chains only
-  struct In { uint4 a; uint4 c[NCA]; };
+  struct In { uint4 a; uint4 c[NCA]; uint4 cnt[CQ]; };
 
   static __device__ __forceinline__ uint4 ld16(const T* base, size_t g) {
     return __ldcs(reinterpret_cast<const uint4*>(base) + g);
@@ -145,7 +164,12 @@ struct IntChainOp {
     In r;
     r.a = ld16(in, g);
 #pragma unroll
-    for (int k = 0; k < NC; ++k) r.c[k] = ld16((const T*)p.cols[k], g);
+    for (int k = 0; k < NC; ++k)
+      if (k < p.n_cols) r.c[k] = ld16((const T*)p.cols[k], g);  // NC may exceed n_cols in the shift variants
+    if constexpr (SH) {
+#pragma unroll
+      for (int q = 0; q < CQ; ++q) r.cnt[q] = __ldcs(reinterpret_cast<const uint4*>(p.counts) + g * CQ + q);
+    }
     return r;
   }
   static constexpr bool JOINT = true;  // all granules of a full tile share one pass over the steps
@@ -167,6 +191,21 @@ struct IntChainOp {
       if (kind == AGPU_STEP_UNARY) {
         words_unary<T, 4 * U>(p.op[s], acc);
         continue;
+      }
+      if constexpr (SH) {
+        if (kind == AGPU_STEP_SHIFT_COLUMN) {
+          constexpr int L = 4 / sizeof(T);
+          const bool left = p.op[s] == AGPU_SHL;
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            uint32_t c[G];  // the granule's counts, row order
+            memcpy(c, inu[j].cnt, sizeof(c));
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              acc[4 * j + w] = left ? shift_lanes<T, true>(acc[4 * j + w], c + w * L) : shift_lanes<T, false>(acc[4 * j + w], c + w * L);
+          }
+          continue;
+        }
       }
       if (kind == AGPU_STEP_BINARY_DEVSCALAR || kind == AGPU_STEP_COMPARE_DEVSCALAR) {
         const uint32_t v = w_splat<T>(__ldg((const T*)p.dscalar[s]));
@@ -223,9 +262,15 @@ struct IntChainOp {
     const uint32_t v = w_splat<T>(in[i]);
     r.a = make_uint4(v, v, v, v);
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const uint32_t w = w_splat<T>(((const T*)p.cols[c])[i]);
-      r.c[c] = make_uint4(w, w, w, w);
+    for (int c = 0; c < NC; ++c)
+      if (c < p.n_cols) {
+        const uint32_t w = w_splat<T>(((const T*)p.cols[c])[i]);
+        r.c[c] = make_uint4(w, w, w, w);
+      }
+    if constexpr (SH) {
+      const uint32_t k = p.counts[i];
+#pragma unroll
+      for (int q = 0; q < CQ; ++q) r.cnt[q] = make_uint4(k, k, k, k);
     }
     return r;
   }
@@ -257,24 +302,31 @@ struct IntChainOp {
   }
 };
 
-template <typename T, int NC>
-int run_int_chain_nc(agpu_device* dev, const IntChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm,
+template <typename T, int NC, bool SH>
+int run_int_chain_as(agpu_device* dev, const IntChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm,
                      bool is_pred) {
-  IntChainOp<T, NC> op{p, (const T*)in, (T*)out};
-  bool al = aligned16(in) && aligned16(out);
+  using Op = IntChainOp<T, NC, SH>;
+  Op op{p, (const T*)in, (T*)out};
+  bool al = aligned16(in) && aligned16(out) && (!SH || aligned16(p.counts));
   for (int k = 0; k < p.n_cols; ++k) al = al && aligned16(p.cols[k]);
-  if (is_pred) return launch_bits<IntChainOp<T, NC>, 2>(dev, op, (uint32_t*)out, n, bm, al);
-  return launch_ew<IntChainOp<T, NC>, 2>(dev, op, n, bm, al);
+  // 1-byte rows with a shift carry 64 bytes of counts per granule: one granule per thread
+  constexpr int UNROLL = (SH && sizeof(T) == 1) ? 1 : 2;
+  if (is_pred) return launch_bits<Op, UNROLL>(dev, op, (uint32_t*)out, n, bm, al);
+  return launch_ew<Op, UNROLL>(dev, op, n, bm, al);
 }
 
 template <typename T>
 int run_int_chain(agpu_device* dev, const IntChainProgram& p, const void* in, void* out, size_t n, const BmAnd& bm,
                   bool is_pred) {
+  if (p.counts) {  // shift variants: column-free or generic, to bound the number of kernels
+    if (p.n_cols == 0) return run_int_chain_as<T, 0, true>(dev, p, in, out, n, bm, is_pred);
+    return run_int_chain_as<T, kMaxCols - 1, true>(dev, p, in, out, n, bm, is_pred);
+  }
   switch (p.n_cols) {
-    case 0: return run_int_chain_nc<T, 0>(dev, p, in, out, n, bm, is_pred);
-    case 1: return run_int_chain_nc<T, 1>(dev, p, in, out, n, bm, is_pred);
-    case 2: return run_int_chain_nc<T, 2>(dev, p, in, out, n, bm, is_pred);
-    default: return run_int_chain_nc<T, 3>(dev, p, in, out, n, bm, is_pred);
+    case 0: return run_int_chain_as<T, 0, false>(dev, p, in, out, n, bm, is_pred);
+    case 1: return run_int_chain_as<T, 1, false>(dev, p, in, out, n, bm, is_pred);
+    case 2: return run_int_chain_as<T, 2, false>(dev, p, in, out, n, bm, is_pred);
+    default: return run_int_chain_as<T, 3, false>(dev, p, in, out, n, bm, is_pred);
   }
 }
 
@@ -289,6 +341,8 @@ extern "C" int agpu_fused_chain_int(agpu_device* dev, int dtype, const void* in,
   IntChainProgram p{};
   p.n_steps = n_steps;
   const uint32_t* vals[4] = {vin, nullptr, nullptr, nullptr};
+  const uint32_t* col_validity[kMaxCols] = {nullptr, nullptr, nullptr};
+  const uint32_t* counts_validity = nullptr;
   bool is_pred = false;
   for (int s = 0; s < n_steps; ++s) {
     const agpu_chain_step& st = steps[s];
@@ -309,6 +363,10 @@ extern "C" int agpu_fused_chain_int(agpu_device* dev, int dtype, const void* in,
         if (s != n_steps - 1) return AGPU_EINVAL;  // a predicate ends the chain
         is_pred = true;
         break;
+      case AGPU_STEP_SHIFT_COLUMN:
+        if (st.op != AGPU_SHL && st.op != AGPU_SHR) return AGPU_EUNSUPPORTED;
+        if (p.counts || dtype == AGPU_DATE32) return AGPU_EUNSUPPORTED;  // one shift step per chain
+        break;
       case AGPU_STEP_BINARY_SCALAR:
       case AGPU_STEP_COMPARE_SCALAR:
         return AGPU_EUNSUPPORTED;  // the float immediate cannot hold every i32/u32: use a device scalar
@@ -317,12 +375,19 @@ extern "C" int agpu_fused_chain_int(agpu_device* dev, int dtype, const void* in,
     if (!st.operand && st.kind != AGPU_STEP_UNARY) return AGPU_EINVAL;
     if (st.kind == AGPU_STEP_BINARY_DEVSCALAR || st.kind == AGPU_STEP_COMPARE_DEVSCALAR) p.dscalar[s] = st.operand;
     if (st.kind == AGPU_STEP_BINARY_COLUMN || st.kind == AGPU_STEP_COMPARE_COLUMN) {
-      if (p.n_cols == kMaxCols) return AGPU_EUNSUPPORTED;
+      if (p.n_cols + (p.counts ? 1 : 0) == kMaxCols) return AGPU_EUNSUPPORTED;
       p.cols[p.n_cols] = st.operand;
-      vals[1 + p.n_cols] = st.validity;
+      col_validity[p.n_cols] = st.validity;
       ++p.n_cols;
     }
+    if (st.kind == AGPU_STEP_SHIFT_COLUMN) {
+      if (p.n_cols == kMaxCols) return AGPU_EUNSUPPORTED;  // columns + counts share the three bitmap slots
+      p.counts = (const uint32_t*)st.operand;
+      counts_validity = st.validity;
+    }
   }
+  for (int k = 0; k < p.n_cols; ++k) vals[1 + k] = col_validity[k];
+  if (p.counts) vals[1 + p.n_cols] = counts_validity;
   if (vout && !vals[0] && !vals[1] && !vals[2] && !vals[3]) return AGPU_EINVAL;
   const BmAnd bm = make_bm(vals[0], vals[1], vals[2], vals[3], vout);
   switch (dtype) {

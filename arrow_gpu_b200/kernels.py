@@ -761,6 +761,7 @@ def fused_chain(data, steps):
 
 
 _INT_CHAIN_UNARY = {"bitwise_not": _ffi.NOT, "abs": _ffi.ABS}
+_INT_CHAIN_SHIFT = {"bitwise_shl": _ffi.SHL, "bitwise_shr": _ffi.SHR}
 _INT_CHAIN_BINARY = {"add": _ffi.ADD, "sub": _ffi.SUB, "mul": _ffi.MUL, "div": _ffi.DIV, "rem": _ffi.REM,
                      "min": _ffi.MIN, "max": _ffi.MAX, "bitwise_and": _ffi.AND, "bitwise_or": _ffi.OR,
                      "bitwise_xor": _ffi.XOR, "power": _ffi.POW}
@@ -772,6 +773,7 @@ def fused_chain_int_op(data, steps, pipeline):
     the column's width, x/0 = x, x%0 = 0).  Steps:
          ("bitwise_not",)  ("abs",)  [abs: Int32 only]
          ("add", other) ... sub mul div rem min max bitwise_and bitwise_or bitwise_xor power [Int32]
+         ("bitwise_shl", counts)  ("bitwise_shr", counts)   counts = UInt32ArrayGPU, one shift per chain
          ("gt", other) ... gteq lt lteq eq          (only as the last step) -> BooleanArrayGPU
     `other` = a column of the same type and length, a DeviceScalar / one-element array of the same
     type, or a python int (uploaded as a one-element array)."""
@@ -789,6 +791,14 @@ def fused_chain_int_op(data, steps, pipeline):
             raise Panic(f"fused_chain_int: {name} not supported for type {data.get_dtype()}")   # math/src/i32.rs
         if name in _INT_CHAIN_UNARY and operand is None:
             arr[k].kind, arr[k].op = _ffi.STEP_UNARY, _INT_CHAIN_UNARY[name]
+            continue
+        if name in _INT_CHAIN_SHIFT:
+            if not isinstance(operand, UInt32ArrayGPU) or isinstance(data, Date32ArrayGPU):
+                raise Panic(f"fused_chain_int: {name} takes a UInt32ArrayGPU of per-row counts")
+            _check_same_len(data, operand, "fused_chain_int")
+            arr[k].kind, arr[k].op = _ffi.STEP_SHIFT_COLUMN, _INT_CHAIN_SHIFT[name]
+            arr[k].operand, arr[k].validity = operand.data.ptr, _vptr(operand.null_buffer)
+            validities.append(operand.null_buffer)
             continue
         if name in _INT_CHAIN_BINARY:
             op, kinds = _INT_CHAIN_BINARY[name], (_ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_DEVSCALAR)
@@ -896,6 +906,15 @@ def _try_fuse_int(base, self, operand, pipeline):
         return _lazy_array(*_extend(self, (base,), pipeline, "int"), pipeline, "int")
     if base == "abs" and operand is None and isinstance(self, Int32ArrayGPU):
         return _lazy_array(*_extend(self, (base,), pipeline, "int"), pipeline, "int")
+    if base in _INT_CHAIN_SHIFT:
+        if not isinstance(operand, UInt32ArrayGPU) or operand.len != self.len:
+            return None
+        lazy = self._lazy
+        if lazy is not None and lazy.mode == "int" and any(st[0] in _INT_CHAIN_SHIFT for st in lazy.steps):
+            source, steps = self, [(base, operand)]      # one shift per kernel: start a new chain here
+        else:
+            source, steps = _extend(self, (base, operand), pipeline, "int")
+        return _lazy_array(source, steps, pipeline, "int")
     if type(operand) is not type(self):
         return None
     if base in _FUSE_SCALAR:

@@ -236,7 +236,10 @@ typedef enum {
   /* rhs = a ONE-element f32 array on the device (how the reference passes scalars:
    * arithmetic/src/lib.rs:11-50); `operand` points at it, no host round trip */
   AGPU_STEP_BINARY_DEVSCALAR = 5,
-  AGPU_STEP_COMPARE_DEVSCALAR = 6
+  AGPU_STEP_COMPARE_DEVSCALAR = 6,
+  /* agpu_fused_chain_int only: acc = acc << / >> counts[i]; op = AGPU_SHL / AGPU_SHR, operand = a
+   * u32 column of per-row counts (logical/src/lib.rs:160-186), validity = its bitmap */
+  AGPU_STEP_SHIFT_COLUMN = 7
 } agpu_step_kind;
 typedef struct {
   int32_t kind;             /* agpu_step_kind */
@@ -256,6 +259,8 @@ int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, const uint3
  * by one (logical/src/lib.rs:120-158, arithmetic/src/lib.rs:11-94, compare/src/lib.rs:142-172).
  *   AGPU_STEP_UNARY              NOT (ABS for I32)
  *   AGPU_STEP_BINARY_COLUMN / _DEVSCALAR   ADD SUB MUL DIV REM MIN MAX AND OR XOR (POW for I32)
+ *   AGPU_STEP_SHIFT_COLUMN                 SHL SHR by a u32 counts column (count & 31 on the widened lane);
+ *                                          one shift step per chain, columns + counts <= 3
  *   AGPU_STEP_COMPARE_COLUMN / _DEVSCALAR  GT GTEQ LT LTEQ EQ, last step only; out is a bitmap
  * Immediates (*_SCALAR steps) are not accepted: the float field cannot hold every 32-bit integer. */
 int agpu_fused_chain_int(agpu_device* dev, int dtype, const void* in, const uint32_t* vin,

@@ -532,6 +532,9 @@ INT_CHAINS = [
     [("mul", "col"), ("div", "scalar"), ("rem", "scalar"), ("bitwise_xor", "col"), ("gt", "col")],
     [("bitwise_or", "scalar"), ("div", "col"), ("lteq", "scalar")],
     [("rem", "col"), ("eq", "col")],
+    [("bitwise_shl", "cnt"), ("add", "col")],
+    [("add", "col"), ("bitwise_shr", "cnt"), ("bitwise_and", "scalar"), ("gt", "col")],
+    [("bitwise_not",), ("bitwise_shr", "cnt")],
 ]
 
 
@@ -547,6 +550,14 @@ def test_fused_chain_int_equals_unfused_and_oracle(chain, dtype, device):
             if len(step) == 1:
                 want, o = getattr(want, name)(), oracle_unary(name, o)
                 steps.append(step)
+                continue
+            if step[1] == "cnt":          # per-row u32 counts, above the lane width too (the `& 31` rule)
+                cnt = rng.integers(0, 40, n).astype(np.uint32)
+                cvalid = rng.random(n) < 0.9 if rng.random() < 0.5 else None
+                gc = ag.UInt32ArrayGPU.from_numpy(cnt, cvalid, device)
+                oc = OArr(O.U32, cnt, n, None if cvalid is None else O.pack_bits(cvalid))
+                steps.append((name, gc))
+                want, o = getattr(want, name)(gc), oracle_binary(name, o, oc)
                 continue
             if step[1] == "col":
                 g, og = make(rng, dtype, n, bool(rng.random() < 0.5), device)
@@ -595,6 +606,10 @@ def test_fused_chain_int_limits(device):
     with pytest.raises(ag.Panic):
         K.fused_chain_int(a, [("abs",)])                    # abs is an Int32 op (math/src/i32.rs)
     assert K.fused_chain_int(a, [("add", 5), ("mul", a)]).raw_values().tolist() == [6, 14, 24]
+    cnt = ag.UInt32ArrayGPU.from_slice([1, 2, 35], device)
+    assert K.fused_chain_int(a, [("bitwise_shl", cnt), ("add", 1)]).raw_values().tolist() == [3, 9, 25]   # 35 & 31 = 3
+    with pytest.raises(ag._ffi.AgpuError):
+        K.fused_chain_int(a, [("bitwise_shl", cnt), ("bitwise_shr", cnt)])      # one shift step per chain
     i32 = ag.Int32ArrayGPU.from_slice([-3, 2, -2**31], device)
     assert K.fused_chain_int(i32, [("abs",), ("power", ag.Int32ArrayGPU.from_slice([2, 3, 1], device))]).raw_values().tolist() \
         == [9, 8, -2**31]
