@@ -76,3 +76,16 @@ tf = timeit(lambda: K.fused_chain(u8, [("mul", K.DeviceScalar(sf)), ("add", K.De
 tu = timeit(lambda: u8.cast(ag.Float32ArrayGPU).mul_scalar(sf).add_scalar(sf))
 print(f"u8   [cast f32, mul s, add s      ] fused {tf:.4f} ms ({5 * n / tf / 1e6:7.1f} GB/s, frac {5 * n / tf / 1e6 / PEAK:.3f})"
       f"   unfused {tu:.4f} ms   speed-up {tu / tf:.2f}x")
+
+# shift by a per-row u32 counts column inside a chain (i8: 1 + 4 + 1 + 1 = 7 B/row; u16: 2 + 4 + 2 + 2 = 10)
+tc = torch.randint(0, 8, (n,), dtype=torch.int32, device="cuda", generator=g)
+cnt = ag.UInt32ArrayGPU(ag.ArrowGpuBuffer(dev, tc.data_ptr(), n * 4, owned=False), dev, n, None)
+for name, cls, tdt, es in (("i8", ag.Int8ArrayGPU, torch.int8, 1), ("u16", ag.UInt16ArrayGPU, torch.int16, 2)):
+    keep = [column(cls, tdt) for _ in range(2)]
+    a, b = (k[1] for k in keep)
+    steps = [("bitwise_shl", cnt), ("add", b)]
+    tf = timeit(lambda: K.fused_chain_int(a, steps))
+    tu = timeit(lambda: a.bitwise_shl(cnt).add(b))
+    bpr = 3 * es + 4
+    print(f"{name:4s} [shl cnt, add b          ] fused {tf:.4f} ms ({bpr * n / tf / 1e6:7.1f} GB/s, frac {bpr * n / tf / 1e6 / PEAK:.3f})"
+          f"   unfused {tu:.4f} ms   speed-up {tu / tf:.2f}x")
