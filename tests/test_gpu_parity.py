@@ -318,6 +318,14 @@ def test_fused_mul_add_gt(device):
 
 
 # ---- sum: same tree order as the reference => bit-identical f32 result ---------------------------
+def test_sum_of_an_empty_column_is_zero(device):
+    """the reference's `while new_length != 1` loop never ends for len 0 (aggregate_kernels.rs:26-44);
+    both sides here define the result as 0"""
+    for cls, dt in ((ag.Float32ArrayGPU, O.F32), (ag.Int32ArrayGPU, O.I32), (ag.UInt32ArrayGPU, O.U32)):
+        got = cls.from_numpy(np.zeros(0, O.NP[dt]), None, device).sum().raw_values()
+        assert got.tolist() == [0] and np.asarray(O.sum(dt, np.zeros(0, O.NP[dt]))).item() == 0
+
+
 def test_sum_bit_exact(device):
     rng = np.random.default_rng(40)
     for n in (1, 255, 256, 257, 65536, 65537, 1_000_003, 5_000_000):
