@@ -1,0 +1,167 @@
+"""CPU: the recording / auto-fusion logic of the host mirror (kernels.py) against a STUB of the C
+ABI that only records calls.  No kernel runs and no result is computed here — the stub exists so
+that the chain-building rules (what is recorded, where a chain ends, how many kernels a recorded
+program becomes) are checked on every CPU run; the numerics of the same programs are checked on
+the GPU (test_gpu_parity.py, test_gpu_fuzz.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import arrow_gpu_b200 as ag
+from arrow_gpu_b200 import _ffi
+from arrow_gpu_b200 import kernels as K
+
+pytestmark = pytest.mark.timeout(120)
+
+LAUNCHING = ("agpu_binary", "agpu_scalar", "agpu_unary", "agpu_compare", "agpu_shift", "agpu_cast", "agpu_fused_chain",
+             "agpu_fused_chain_int", "agpu_fused_mul_add_gt", "agpu_bitmap_binary", "agpu_bitmap_not", "agpu_merge",
+             "agpu_take")
+
+
+class StubLib:
+    """records (name, args); fills the out-parameters of the allocation / creation calls"""
+
+    def __init__(self):
+        self.calls, self._next = [], 0x10000
+
+    def _ptr(self):
+        self._next += 0x1000
+        return self._next
+
+    def __getattr__(self, name):
+        def fn(*args):
+            if name in ("agpu_device_create", "agpu_alloc", "agpu_event_create", "agpu_host_alloc"):
+                args[-1]._obj.value = self._ptr()
+            elif name == "agpu_launch_count":
+                return sum(1 for n, _a in self.calls if n in LAUNCHING)
+            if name.startswith("agpu_fused_chain"):
+                steps = [(st.kind, st.op, st.operand, st.scalar) for st in list(args[4])[: args[5]]]
+                self.calls.append((name, steps))
+            else:
+                self.calls.append((name, args))
+            return 0
+        return fn
+
+    def launched(self):
+        return [(n, a) for n, a in self.calls if n in LAUNCHING]
+
+
+@pytest.fixture
+def stub(monkeypatch):
+    lib = StubLib()
+    monkeypatch.setattr(_ffi, "_lib", lib)
+    dev = ag.GpuDevice(0)
+    yield lib, dev
+    dev.handle = None            # nothing to destroy
+
+
+def f32(dev, n=64):
+    return ag.Float32ArrayGPU.from_slice([1.0] * n, dev)
+
+
+def test_plain_pipeline_launches_every_op(stub):
+    lib, dev = stub
+    a, b, s = f32(dev), f32(dev), f32(dev, 1)
+    p = ag.ArrowComputePipeline(dev)
+    K.gt_op_dyn(K.add_op_dyn(K.mul_scalar_op_dyn(a, s, p), b, p), b, p)
+    p.finish()
+    assert [n for n, _ in lib.launched()] == ["agpu_scalar", "agpu_binary", "agpu_compare"]
+
+
+def test_fusing_pipeline_records_one_chain(stub):
+    lib, dev = stub
+    a, b, s = f32(dev), f32(dev), f32(dev, 1)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    r = K.sqrt_op_dyn(K.add_op_dyn(K.mul_scalar_op_dyn(a, s, p), b, p), p)
+    assert lib.launched() == []                               # nothing runs while recording
+    p.finish()
+    (name, steps), = lib.launched()
+    assert name == "agpu_fused_chain"
+    assert [(k, o) for k, o, _p, _s in steps] == [(_ffi.STEP_BINARY_DEVSCALAR, _ffi.MUL), (_ffi.STEP_BINARY_COLUMN, _ffi.ADD),
+                                                  (_ffi.STEP_UNARY, _ffi.SQRT)]
+    assert steps[0][2] == s.data.ptr and steps[1][2] == b.data.ptr
+    assert r.len == a.len
+
+
+def test_compare_ends_and_launches_the_chain_at_once(stub):
+    lib, dev = stub
+    a, b = f32(dev), f32(dev)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    m = K.lteq_op_dyn(K.mul_op_dyn(a, b, p), b, p)
+    (name, steps), = lib.launched()                           # before finish()
+    assert name == "agpu_fused_chain" and steps[-1][:2] == (_ffi.STEP_COMPARE_COLUMN, _ffi.LTEQ)
+    assert isinstance(m, ag.BooleanArrayGPU)
+    p.finish()
+    assert len(lib.launched()) == 1
+
+
+def test_chain_limits_split_into_more_kernels(stub):
+    lib, dev = stub
+    a = f32(dev)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    r = a
+    for _ in range(_ffi.CHAIN_MAX_STEPS + 3):                 # 11 unary steps -> 8 + 3
+        r = K.abs_op_dyn(r, p)
+    p.finish()
+    assert [len(steps) for _n, steps in lib.launched()] == [8, 3]
+    lib.calls.clear()
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    r = a
+    cols = [f32(dev) for _ in range(5)]
+    for c in cols:                                            # 5 operand columns -> 3 + 2
+        r = K.add_op_dyn(r, c, p)
+    p.finish()
+    assert [len(steps) for _n, steps in lib.launched()] == [3, 2]
+
+
+def test_reading_a_recorded_array_launches_it_on_demand(stub):
+    lib, dev = stub
+    a, b = f32(dev), f32(dev)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    r = K.add_op_dyn(a, b, p)
+    assert lib.launched() == []
+    assert r.data.ptr                                          # touching the buffer materialises the chain
+    assert [n for n, _ in lib.launched()] == ["agpu_fused_chain"]
+    p.finish()
+    assert len(lib.launched()) == 1                            # not launched twice
+
+
+def test_integer_chains_and_the_one_shift_rule(stub):
+    lib, dev = stub
+    a = ag.Int8ArrayGPU.from_slice([1] * 32, dev)
+    b = ag.Int8ArrayGPU.from_slice([2] * 32, dev)
+    s = ag.Int8ArrayGPU.from_slice([3], dev)
+    cnt = ag.UInt32ArrayGPU.from_slice([1] * 32, dev)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    r = K.bitwise_and_op_dyn(K.add_op_dyn(a, b, p), b, p)
+    r = K.mul_scalar_op_dyn(r, s, p)
+    r = K.bitwise_shl_op_dyn(r, cnt, p)
+    r2 = K.bitwise_shr_op_dyn(r, cnt, p)                       # a second shift starts a new chain
+    p.finish()
+    launched = lib.launched()
+    assert [n for n, _ in launched] == ["agpu_fused_chain_int", "agpu_fused_chain_int"]
+    assert [k for k, *_ in launched[0][1]] == [_ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_DEVSCALAR,
+                                               _ffi.STEP_SHIFT_COLUMN]
+    assert [(k, o) for k, o, *_ in launched[1][1]] == [(_ffi.STEP_SHIFT_COLUMN, _ffi.SHR)]
+    assert isinstance(r2, ag.Int8ArrayGPU)
+
+
+def test_modes_do_not_mix_and_ineligible_ops_fall_back(stub):
+    lib, dev = stub
+    i8 = ag.Int8ArrayGPU.from_slice([1] * 32, dev)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    t = K.bitwise_not_op_dyn(i8, p)                            # int-mode chain
+    u = K.sin_op_dyn(t, p)                                     # f32-mode chain starting at the recorded int array
+    p.finish()
+    names = [n for n, _ in lib.launched()]
+    assert names == ["agpu_fused_chain_int", "agpu_fused_chain"], names
+    assert isinstance(u, ag.Float32ArrayGPU)
+    lib.calls.clear()
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    other = ag.Int16ArrayGPU.from_slice([1] * 32, dev)
+    with pytest.raises(ag.Panic):
+        K.add_op_dyn(i8, other, p)                             # type mismatch is still the reference's panic
+    m = ag.BooleanArrayGPU.from_slice([True] * 32, dev)
+    K.merge_op_dyn(K.bitwise_not_op_dyn(i8, p), i8, m, p)      # merge is not fusable: its lazy operand is launched first
+    assert [n for n, _ in lib.launched()] == ["agpu_fused_chain_int", "agpu_merge"]
