@@ -35,6 +35,9 @@ class StubLib:
                 args[-1]._obj.value = self._ptr()
             elif name == "agpu_launch_count":
                 return sum(1 for n, _a in self.calls if n in LAUNCHING)
+            if name == "agpu_h2d":                              # keep the uploaded bytes: (dst, bytes)
+                self.calls.append((name, (args[1], C.string_at(args[2], args[3]))))
+                return 0
             if name.startswith("agpu_fused_chain"):
                 steps = [(st.kind, st.op, st.operand, st.scalar) for st in list(args[4])[: args[5]]]
                 self.calls.append((name, steps))
@@ -165,3 +168,25 @@ def test_modes_do_not_mix_and_ineligible_ops_fall_back(stub):
     m = ag.BooleanArrayGPU.from_slice([True] * 32, dev)
     K.merge_op_dyn(K.bitwise_not_op_dyn(i8, p), i8, m, p)      # merge is not fusable: its lazy operand is launched first
     assert [n for n, _ in lib.launched()] == ["agpu_fused_chain_int", "agpu_merge"]
+
+
+def test_constructors_upload_the_reference_layout(stub):
+    """primitive_array_gpu.rs:22-55, boolean_gpu.rs:23-50, null_bit_buffer.rs:10-62: dense
+    little-endian values with T::default() in the null slots, LSB-first bitmaps padded to whole
+    32-bit words with zero padding bits"""
+    lib, dev = stub
+    a = ag.Int16ArrayGPU.from_optional_slice([5, None, -2, None, 7], dev)
+    uploads = {dst: data for n, (dst, data) in [(n, x) for n, x in lib.calls if n == "agpu_h2d"]}
+    assert np.frombuffer(uploads[a.data.ptr], dtype="<i2").tolist() == [5, 0, -2, 0, 7]
+    assert uploads[a.null_buffer.bit_buffer.ptr] == bytes([0b10101, 0, 0, 0])
+    lib.calls.clear()
+    flags = [True, False, None, True] + [True] * 30                      # 34 bits -> two words
+    b = ag.BooleanArrayGPU.from_optional_slice(flags, dev)
+    uploads = {dst: data for n, (dst, data) in [(n, x) for n, x in lib.calls if n == "agpu_h2d"]}
+    data, valid = uploads[b.data.ptr], uploads[b.null_buffer.bit_buffer.ptr]
+    assert len(data) == 8 and len(valid) == 8
+    assert data[0] == 0b11111001 and data[4] == 0b11 and data[5:] == bytes(3)
+    assert valid[0] == 0b11111011 and valid[4] == 0b11
+    assert b.len == 34 and a.len == 5
+    f = ag.Float32ArrayGPU.from_slice([1.0, -0.0], dev)
+    assert f.null_buffer is None                                         # no nulls -> no bitmap (null_bit_buffer.rs:99-111)
