@@ -79,17 +79,16 @@ def test_arrow_c_data_interface_roundtrip():
 
 
 @pytest.mark.gpu
-def test_reference_example_in_python_and_cpp():
-    """crates/arrow/examples/simple.rs transcribed twice (examples/simple.py, examples/simple.cpp):
-    same calls, same assertions"""
+def test_examples_run():
+    """examples/scalar_ops.{py,cpp}: the usage styles of the reference's own example on both host mirrors"""
     import sys
     ex = os.path.join(ROOT, "examples")
-    res = subprocess.run([sys.executable, os.path.join(ex, "simple.py")], capture_output=True, text=True, timeout=300)
+    res = subprocess.run([sys.executable, os.path.join(ex, "scalar_ops.py")], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "example ok: recorded pipeline = 2 kernel launches, fusing pipeline = 1" in res.stdout
-    exe = os.path.join(ex, "simple")
-    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + CPP, os.path.join(ex, "simple.cpp"),
+    assert "scalar_ops ok: 2 kernels recorded one by one, 1 on a fusing pipeline" in res.stdout
+    exe = os.path.join(ex, "scalar_ops")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + CPP, os.path.join(ex, "scalar_ops.cpp"),
                     "-L" + os.path.join(ROOT, "arrow_gpu_b200", "lib"), "-lagpu",
                     "-Wl,-rpath," + os.path.join(ROOT, "arrow_gpu_b200", "lib"), "-o", exe], check=True)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0 and "example ok" in res.stdout, res.stdout + res.stderr
+    assert res.returncode == 0 and "scalar_ops ok" in res.stdout, res.stdout + res.stderr
