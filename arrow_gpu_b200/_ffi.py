@@ -35,7 +35,16 @@ SIGNATURES = {
     "agpu_error_string": (C.c_char_p, [_i]),
     "agpu_alloc": (_i, [_p, _sz, C.POINTER(_p)]),
     "agpu_free": (_i, [_p, _p]),
+    "agpu_buffer_record_use": (_i, [_p, _p]),
     "agpu_trim": (_i, [_p]),
+    "agpu_graph_begin": (_i, [_p]),
+    "agpu_graph_end": (_i, [_p, C.POINTER(_p)]),
+    "agpu_graph_launch": (_i, [_p, _p]),
+    "agpu_graph_kernel_count": (C.c_uint64, [_p]),
+    "agpu_graph_destroy": (_i, [_p]),
+    "agpu_exchange_bytes": (_sz, [_i]),
+    "agpu_exchange_post": (_i, [_p, _p, C.POINTER(_p), _i, _i, C.c_uint32]),
+    "agpu_exchange_wait": (_i, [_p, _p, _i, C.c_uint32, _p, C.c_uint32]),
     "agpu_h2d": (_i, [_p, _p, _p, _sz]),
     "agpu_d2h": (_i, [_p, _p, _p, _sz]),
     "agpu_d2h_async": (_i, [_p, _p, _p, _sz]),
@@ -61,10 +70,10 @@ SIGNATURES = {
     "agpu_fused_mul_add_gt": (_i, [_p, _p, _p, _p, _p, _u32p, _sz, _u32p, _u32p, _u32p, _u32p, _u32p]),
     "agpu_merge": (_i, [_p, _i, _p, _p, _u32p, _p, _sz, _u32p, _u32p, _u32p, _u32p]),
     "agpu_take": (_i, [_p, _i, _p, _sz, _u32p, _p, _sz, _u32p, _u32p]),
-    "agpu_put": (_i, [_p, _i, _p, _u32p, _p, _u32p, _sz]),
+    "agpu_put": (_i, [_p, _i, _p, _sz, _u32p, _p, _sz, _u32p, _sz]),
     "agpu_filter_scratch_bytes": (_sz, [_sz]),
     "agpu_filter_count": (_i, [_p, _u32p, _u32p, _sz, _p, _p]),
-    "agpu_filter_scatter": (_i, [_p, _i, _p, _u32p, _u32p, _u32p, _sz, _p, _p, _u32p]),
+    "agpu_filter_scatter": (_i, [_p, _i, _p, _u32p, _u32p, _u32p, _sz, _p, _p, _u32p, _sz]),
     "agpu_ipc_alloc": (_i, [_p, _sz, C.POINTER(_p)]),
     "agpu_ipc_free": (_i, [_p, _p]),
     "agpu_ipc_export": (_i, [_p, _p, C.c_char_p]),

@@ -197,6 +197,13 @@ class GpuDevice:
     def launch_count(self) -> int:
         return int(lib().agpu_launch_count(self.handle))
 
+    def record_use(self, buffer: "ArrowGpuBuffer") -> None:
+        """this handle has enqueued (or is about to enqueue) work on a buffer that ANOTHER handle of
+        the same GPU allocated: when the buffer is dropped, its block only returns to the owner's
+        cache after this handle's stream got there (agpu_buffer_record_use; wgpu keeps a buffer
+        alive until submitted work is done, buffer.rs:5-7)"""
+        check(lib().agpu_buffer_record_use(self.handle, buffer.ptr), "agpu_buffer_record_use")
+
 
 class GpuEvent:
     def __init__(self):
@@ -233,6 +240,10 @@ class ArrowGpuBuffer:
         """bytes (buffer.rs:22-24)"""
         return self._size
 
+    def free(self) -> None:
+        """explicit drop (idempotent; __del__ does the same)"""
+        self.__del__()
+
     def __del__(self):
         try:
             if self._owned and self.ptr and self.device.handle and not _SHUTDOWN:
@@ -250,10 +261,17 @@ class ArrowGpuBuffer:
 class ArrowComputePipeline:
     """gpu_utils/compute_pipeline.rs:8-22.  The reference records compute passes into one
     wgpu CommandEncoder and submits them in `finish()`.  CUDA streams are already ordered
-    queues, so every `*_op` enqueues its kernel immediately on the device's stream and
-    `finish()` only marks the end of the scope (it never waits, like the reference)."""
+    queues, so by default every `*_op` enqueues its kernel immediately on the device's stream and
+    `finish()` only marks the end of the scope (it never waits, like the reference).
 
-    def __init__(self, device: GpuDevice, label: Optional[str] = None, profile: bool = False, fuse: bool = False):
+    capture=True is the literal analogue of record-then-submit: the ops recorded between the
+    constructor and `finish()` are captured into a CUDA graph (agpu_graph_begin/end) and `finish()`
+    submits the whole program with ONE driver call; `replay()` submits the same recorded program
+    again (same input buffers, outputs overwritten in place) for the cost of one graph launch
+    instead of one launch per op.  Inside a capture nothing may read back to the host."""
+
+    def __init__(self, device: GpuDevice, label: Optional[str] = None, profile: bool = False, fuse: bool = False,
+                 capture: bool = False):
         self.device = device
         self.label = label
         self.finished = False
@@ -267,6 +285,12 @@ class ArrowComputePipeline:
         # (gpu_utils/compute_query.rs:3-90); here: a CUDA event pair per recorded op
         self.profile = profile
         self.queries: list = []
+        self.capture = capture
+        self.graph: Optional["GpuGraph"] = None
+        if capture:
+            if profile:
+                raise ValueError("profile=True records events between ops; it cannot be combined with capture=True")
+            check(lib().agpu_graph_begin(device.handle), "agpu_graph_begin")
 
     @classmethod
     def new(cls, device: GpuDevice, label: Optional[str] = None) -> "ArrowComputePipeline":
@@ -279,15 +303,59 @@ class ArrowComputePipeline:
     def clone_buffer(self, buffer: ArrowGpuBuffer) -> ArrowGpuBuffer:
         return self.device.clone_buffer(buffer)
 
-    def finish(self) -> None:
-        """compute_pipeline.rs:259-273.  With fuse=True this launches one fused kernel per recorded
-        chain whose result is still referenced and was not absorbed into a longer chain."""
+    def flush_recorded(self) -> None:
+        """launch every chain recorded with fuse=True that nothing absorbed (their results must exist
+        before an in-place op such as put_op touches the buffers they read)"""
         for ref in self._lazies:
             arr = ref()
             if arr is not None and arr._lazy is not None and not arr._lazy.consumed:
                 arr._materialize()
         self._lazies = []
+
+    def finish(self) -> None:
+        """compute_pipeline.rs:259-273.  With fuse=True this launches one fused kernel per recorded
+        chain whose result is still referenced and was not absorbed into a longer chain.  With
+        capture=True it ends the capture and submits the recorded program once."""
+        self.flush_recorded()
+        if self.capture and not self.finished:
+            h = C.c_void_p()
+            check(lib().agpu_graph_end(self.device.handle, C.byref(h)), "agpu_graph_end")
+            self.graph = GpuGraph(self.device, h)
+            self.graph.launch()
         self.finished = True
+
+    def replay(self) -> None:
+        """submit the recorded program again (capture=True pipelines, after finish())"""
+        if self.graph is None:
+            raise RuntimeError("replay() needs a pipeline created with capture=True and finished")
+        self.graph.launch()
+
+    def abort(self) -> None:
+        """leave a capture without submitting (error paths)"""
+        if self.capture and not self.finished:
+            h = C.c_void_p()
+            if lib().agpu_graph_end(self.device.handle, C.byref(h)) == 0 and h:
+                lib().agpu_graph_destroy(h)
+            self.finished = True
+
+
+class GpuGraph:
+    """a captured pipeline: agpu_graph (cudaGraphExec_t + the temporaries its kernels write)"""
+
+    def __init__(self, device: GpuDevice, handle):
+        self.device, self.handle = device, handle
+        self.kernels = int(lib().agpu_graph_kernel_count(handle))
+
+    def launch(self) -> None:
+        check(lib().agpu_graph_launch(self.device.handle, self.handle), "agpu_graph_launch")
+
+    def __del__(self):
+        try:
+            if self.handle and self.device.handle and not _SHUTDOWN:
+                lib().agpu_graph_destroy(self.handle)
+        except Exception:
+            pass
+        self.handle = None
 
 
 _PINNED: dict = {}

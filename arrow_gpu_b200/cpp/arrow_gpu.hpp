@@ -367,8 +367,8 @@ class PrimitiveArrayGpu {  // primitive_array_gpu.rs:12-19 (same public fields)
   }
   void put(const UInt32ArrayGPU& src_indexes, PrimitiveArrayGpu& dst, const UInt32ArrayGPU& dst_indexes) const {
     if (null_buffer || dst.null_buffer) throw Panic("put with validity is todo!() in the reference (routines/src/lib.rs:164-169)");
-    check(agpu_put(gpu_device->handle(), DTYPE, data->ptr(), (const uint32_t*)src_indexes.data->ptr(), dst.data->ptr(),
-                   (const uint32_t*)dst_indexes.data->ptr(), src_indexes.len), "put");
+    check(agpu_put(gpu_device->handle(), DTYPE, data->ptr(), len, (const uint32_t*)src_indexes.data->ptr(), dst.data->ptr(),
+                   dst.len, (const uint32_t*)dst_indexes.data->ptr(), src_indexes.len), "put");
   }
   PrimitiveArrayGpu filter(const BooleanArrayGPU& mask) const {  // new surface (BASELINE.json config 5)
     ArrowGpuBuffer scratch(gpu_device, agpu_filter_scratch_bytes(len)), total(gpu_device, 8);
@@ -377,10 +377,10 @@ class PrimitiveArrayGpu {  // primitive_array_gpu.rs:12-19 (same public fields)
     auto raw = total.retrive_data(8);
     std::memcpy(&count, raw.data(), 8);
     Validity nb;
-    if (null_buffer) nb = NullBitBufferGpu{std::make_shared<ArrowGpuBuffer>(gpu_device, bitmap_words(len) * 4 + 4), count, gpu_device};
+    if (null_buffer) nb = NullBitBufferGpu{std::make_shared<ArrowGpuBuffer>(gpu_device, bitmap_words(count) * 4), count, gpu_device};
     auto out = empty(count, gpu_device, nb);
     check(agpu_filter_scatter(gpu_device->handle(), DTYPE, data->ptr(), vptr(null_buffer), mask.bits(), vptr(mask.null_buffer), len,
-                              scratch.ptr(), out.data->ptr(), vptr_mut(out.null_buffer)), "filter_scatter");
+                              scratch.ptr(), out.data->ptr(), vptr_mut(out.null_buffer), count), "filter_scatter");
     return out;
   }
 

@@ -20,6 +20,8 @@ __device__ __forceinline__ uint32_t merge_bit_groups(uint32_t v) {
 template <class Op, int UNROLL>
 __global__ void __launch_bounds__(kBlock) bits_kernel(const Op op, uint32_t* __restrict__ out, const size_t n,
                                                       const BmAnd bm) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int G = Op::G;
   constexpr int S = 32 / G;  // lanes per output word
   const size_t n_gran = n / G;
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(kBlock) bits_kernel(const Op op, uint32_t* __r
 template <class Op>
 __global__ void __launch_bounds__(kBlock) bits_kernel_unaligned(const Op op, uint32_t* __restrict__ out,
                                                                 const size_t n, const BmAnd bm) {
+  pdl_wait();
+  pdl_launch_dependents();
   const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
   const bool p = i < n ? op.bit_at(i) : false;
   const uint32_t w = __ballot_sync(0xFFFFFFFFu, p);
@@ -79,13 +83,13 @@ static int launch_bits(agpu_device* dev, const Op& op, uint32_t* out, size_t n, 
   if (aligned) {
     const size_t grid = ceil_div(n, (size_t)kBlock * UNROLL * Op::G);
     if (grid > 0x7FFFFFFFull) return AGPU_EINVAL;
-    AGPU_LAUNCH(dev, (bits_kernel<Op, UNROLL>), (unsigned)grid, kBlock, 0, op, out, n, bm);
+    AGPU_LAUNCH_PDL(dev, (bits_kernel<Op, UNROLL>), (unsigned)grid, kBlock, 0, op, out, n, bm);
   } else {
     const size_t grid = ceil_div(n, (size_t)kBlock);
     if (grid > 0x7FFFFFFFull) return AGPU_EINVAL;
     BmAnd scalar_bm = bm;
     scalar_bm.vec = 0;
-    AGPU_LAUNCH(dev, (bits_kernel_unaligned<Op>), (unsigned)grid, kBlock, 0, op, out, n, scalar_bm);
+    AGPU_LAUNCH_PDL(dev, (bits_kernel_unaligned<Op>), (unsigned)grid, kBlock, 0, op, out, n, scalar_bm);
   }
   return agpu_finish_launch();
 }

@@ -7,8 +7,11 @@
 #include <map>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/agpu.h"
+
+struct agpu_graph;
 
 struct agpu_device {
   int ordinal;
@@ -16,19 +19,36 @@ struct agpu_device {
   cudaMemPool_t pool;
   unsigned long long launches;  // kernels launched through this handle
   int sm_count;
-  // Stream-ordered caching allocator in front of cudaMallocAsync: every op allocates a fresh
-  // output (like the reference), so freed blocks are kept by size and handed out again without
-  // going back to the driver pool — whose remapping when block sizes alternate costs
-  // milliseconds (measured: profiles/r01_size_sweep.md).  Safe because all work of a handle is
-  // ordered on its one stream: a block freed after op k can only be reused by op k+1 or later.
-  std::mutex mu;
-  std::multimap<size_t, void*> free_blocks;       // size -> block
-  std::unordered_map<void*, size_t> block_size;   // every block handed out or cached
+  // Stream-ordered caching allocator in front of cudaMallocAsync (device.cu): every op allocates
+  // a fresh output (like the reference), so freed blocks are kept by size and handed out again
+  // without going back to the driver pool — whose remapping when block sizes alternate costs
+  // milliseconds (measured: profiles/r01_size_sweep.md).  Reuse is safe because a block only
+  // re-enters its OWNER's cache after the owner's stream has been ordered behind every other
+  // handle that used it (agpu_buffer_record_use + the event wait in agpu_free).
+  // All allocator state of all handles is guarded by one global mutex (device.cu: g_mem_mu).
+  std::multimap<size_t, void*> free_blocks;  // size -> cached block
   size_t cached_bytes = 0;
+  cudaEvent_t order_event = nullptr;         // "this stream's position now", for cross-handle ordering
+  // stream capture (agpu_graph_begin .. agpu_graph_end): blocks freed while capturing stay with the
+  // graph (its kernels write them at every replay), they do not go back to the cache
+  bool capturing = false;
+  unsigned long long capture_launches0 = 0;
+  std::vector<void*> capture_freed;
+  int pdl = 1;                               // programmatic dependent launch for the streaming kernels
 };
 
 struct agpu_event {
   cudaEvent_t ev;
+};
+
+// a captured ArrowComputePipeline: one cudaGraphLaunch replays every kernel recorded between
+// agpu_graph_begin and agpu_graph_end (compute_pipeline.rs:259-273: one submit per pipeline)
+struct agpu_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  agpu_device* dev = nullptr;
+  unsigned long long kernels = 0;   // kernel launches captured
+  std::vector<void*> blocks;        // temporaries freed during the capture: owned until destroy
 };
 
 #define AGPU_CUDA(expr)                          \
@@ -42,12 +62,48 @@ struct agpu_event {
     if (!(cond)) return AGPU_EINVAL;   \
   } while (0)
 
-// Every kernel launch goes through this macro so that agpu_launch_count() is exact.
+// Work is always issued with the handle's device current: a process may hold handles of several
+// ordinals, and a worker thread starts on device 0 (cudaGetDevice is a thread-local read).
+static inline void agpu_make_current(const agpu_device* dev) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != dev->ordinal) cudaSetDevice(dev->ordinal);
+}
+
+// Every kernel launch goes through one of these macros so that agpu_launch_count() is exact.
 #define AGPU_LAUNCH(dev, kernel, grid, block, smem, ...)                       \
   do {                                                                         \
+    agpu_make_current(dev);                                                    \
     kernel<<<(grid), (block), (smem), (dev)->stream>>>(__VA_ARGS__);           \
     (dev)->launches++;                                                         \
   } while (0)
+
+// Programmatic dependent launch (sm_90+): the grid may start while the previous kernel of the
+// stream drains its last wave; the kernel itself executes `griddepcontrol.wait` (pdl_wait())
+// before its first global-memory access, which returns once every earlier grid has completed and
+// its writes are visible.  Launch ramp and tail of back-to-back streaming kernels overlap.
+#define AGPU_LAUNCH_PDL(dev, kernel, grid, block, smem, ...)                                  \
+  do {                                                                                        \
+    agpu_make_current(dev);                                                                   \
+    cudaLaunchConfig_t _cfg = {};                                                             \
+    _cfg.gridDim = dim3(grid);                                                                \
+    _cfg.blockDim = dim3(block);                                                              \
+    _cfg.dynamicSmemBytes = (smem);                                                           \
+    _cfg.stream = (dev)->stream;                                                              \
+    cudaLaunchAttribute _attr[1];                                                             \
+    _attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                         \
+    _attr[0].val.programmaticStreamSerializationAllowed = (dev)->pdl;                         \
+    _cfg.attrs = _attr;                                                                       \
+    _cfg.numAttrs = 1;                                                                        \
+    cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                                           \
+    (dev)->launches++;                                                                        \
+  } while (0)
+
+#ifdef __CUDACC__
+// first statement of every kernel launched with AGPU_LAUNCH_PDL (a no-op for a normal launch)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the next kernel of the stream begin launching; its own pdl_wait() still orders the data
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 static inline int agpu_finish_launch() {
   cudaError_t e = cudaPeekAtLastError();

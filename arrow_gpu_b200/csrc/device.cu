@@ -10,12 +10,22 @@
 
 extern "C" int agpu_abi_version(void) { return AGPU_ABI_VERSION; }
 
-static void release_cache(agpu_device* dev);
-
-// every live handle of this process: on an out-of-memory a handle asks the other handles of the
-// same GPU (e.g. an upload stream's handle) to give their cached blocks back as well
+// ---------------------------------------------------------------------------------------------
+// allocator state shared by every handle of the process
+// ---------------------------------------------------------------------------------------------
+struct Block {
+  size_t size;
+  agpu_device* owner;                // the handle whose cache the block returns to (nullptr: owner destroyed)
+  bool cached;                       // sitting in owner->free_blocks
+  bool from_malloc;                  // cudaMalloc (allocated during a stream capture) instead of the pool
+  std::vector<agpu_device*> users;   // other handles that enqueued work on it (agpu_buffer_record_use)
+};
+static std::mutex g_mem_mu;                      // guards g_blocks and every handle's free_blocks
+static std::unordered_map<void*, Block> g_blocks;  // every block handed out or cached
 static std::mutex g_registry_mu;
-static std::vector<agpu_device*> g_registry;
+static std::vector<agpu_device*> g_registry;     // every live handle
+
+static void release_cache(agpu_device* dev);     // caller holds g_mem_mu
 
 extern "C" int agpu_device_count(int* out) {
   if (!out) return AGPU_EINVAL;
@@ -45,19 +55,21 @@ extern "C" int agpu_device_create(int ordinal, agpu_device** out) {
   d->launches = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete d; return (int)e; }
-  e = cudaDeviceGetDefaultMemPool(&d->pool, ordinal);
+  e = cudaEventCreateWithFlags(&d->order_event, cudaEventDisableTiming);
   if (e != cudaSuccess) { cudaStreamDestroy(d->stream); delete d; return (int)e; }
+  e = cudaDeviceGetDefaultMemPool(&d->pool, ordinal);
+  if (e != cudaSuccess) { cudaEventDestroy(d->order_event); cudaStreamDestroy(d->stream); delete d; return (int)e; }
   // keep freed blocks in the pool: every op allocates a fresh output (like the reference) and
   // the allocation must not cost a cudaMalloc each time
   unsigned long long threshold = ~0ull;
   cudaMemPoolSetAttribute(d->pool, cudaMemPoolAttrReleaseThreshold, &threshold);
   cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, ordinal);
-  // experiment knob: L2 -> DRAM fetch granularity hint in bytes (32/64/128); gathers fetch less
-  // with a small value, streaming kernels request whole lines either way
+  // experiment knobs: L2 -> DRAM fetch granularity hint in bytes (32/64/128), and PDL off
   if (const char* g = getenv("AGPU_L2_FETCH_GRANULARITY")) {
     const size_t v = (size_t)atoi(g);
     if (v) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, v);
   }
+  if (const char* g = getenv("AGPU_PDL")) d->pdl = atoi(g) ? 1 : 0;
   {
     std::lock_guard<std::mutex> lock(g_registry_mu);
     g_registry.push_back(d);
@@ -75,10 +87,17 @@ extern "C" int agpu_device_destroy(agpu_device* dev) {
   }
   cudaSetDevice(dev->ordinal);
   {
-    std::lock_guard<std::mutex> lock(dev->mu);
+    std::lock_guard<std::mutex> lock(g_mem_mu);
     release_cache(dev);
+    for (auto& kv : g_blocks) {  // blocks still alive outlive their handle: freed by whoever drops them
+      Block& b = kv.second;
+      if (b.owner == dev) b.owner = nullptr;
+      for (size_t k = 0; k < b.users.size();)
+        if (b.users[k] == dev) b.users.erase(b.users.begin() + k); else ++k;
+    }
   }
   cudaStreamSynchronize(dev->stream);
+  cudaEventDestroy(dev->order_event);
   cudaStreamDestroy(dev->stream);
   delete dev;
   return 0;
@@ -94,6 +113,8 @@ extern "C" const char* agpu_error_string(int code) {
     case AGPU_EUNSUPPORTED: return "operation not supported for this dtype";
     case AGPU_EINVAL: return "invalid argument";
     case AGPU_ENODEVICE: return "no CUDA device";
+    case AGPU_EDOUBLEFREE: return "buffer freed twice or not allocated by agpu_alloc";
+    case AGPU_ETIMEOUT: return "a peer GPU did not post its value in time";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -106,13 +127,31 @@ static size_t round_block(size_t bytes) {
   return (bytes + gran - 1) / gran * gran;
 }
 
-static void release_cache(agpu_device* dev) {  // caller holds dev->mu
+static void release_block(agpu_device* dev, void* ptr, const Block& b) {
+  if (b.from_malloc) cudaFree(ptr);
+  else cudaFreeAsync(ptr, dev->stream);
+}
+
+static void release_cache(agpu_device* dev) {  // caller holds g_mem_mu
   for (auto& kv : dev->free_blocks) {
-    cudaFreeAsync(kv.second, dev->stream);
-    dev->block_size.erase(kv.second);
+    auto it = g_blocks.find(kv.second);
+    if (it != g_blocks.end()) {
+      release_block(dev, kv.second, it->second);
+      g_blocks.erase(it);
+    }
   }
   dev->free_blocks.clear();
   dev->cached_bytes = 0;
+}
+
+// cudaMalloc is a "potentially unsafe" call while this thread captures a stream: allowed in
+// relaxed mode only, so switch the thread's capture mode around it
+static cudaError_t malloc_during_capture(void** out, size_t bytes) {
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  cudaThreadExchangeStreamCaptureMode(&mode);
+  const cudaError_t e = cudaMalloc(out, bytes);
+  cudaThreadExchangeStreamCaptureMode(&mode);
+  return e;
 }
 
 extern "C" int agpu_alloc(agpu_device* dev, size_t bytes, void** out) {
@@ -120,64 +159,196 @@ extern "C" int agpu_alloc(agpu_device* dev, size_t bytes, void** out) {
   if (!out) return AGPU_EINVAL;
   *out = nullptr;
   const size_t want = round_block(bytes);
-  std::lock_guard<std::mutex> lock(dev->mu);
+  std::lock_guard<std::mutex> lock(g_mem_mu);
   // best fit among cached blocks, but never waste more than 25 % (+1 MiB) of a block
   auto it = dev->free_blocks.lower_bound(want);
   if (it != dev->free_blocks.end() && it->first <= want + want / 4 + (1u << 20)) {
     *out = it->second;
     dev->cached_bytes -= it->first;
     dev->free_blocks.erase(it);
+    g_blocks[*out].cached = false;
     return 0;
   }
-  AGPU_CUDA(cudaSetDevice(dev->ordinal));
-  cudaError_t e = cudaMallocAsync(out, want, dev->stream);
-  if (e == cudaErrorMemoryAllocation) {  // give the caches back to the driver and retry once
+  agpu_make_current(dev);
+  cudaError_t e = dev->capturing ? malloc_during_capture(out, want) : cudaMallocAsync(out, want, dev->stream);
+  if (e == cudaErrorMemoryAllocation && !dev->capturing) {  // give the caches back to the driver and retry once
     cudaGetLastError();
     release_cache(dev);
     {
-      // other handles of the same GPU: try_lock, so two handles running out of memory at the same
-      // moment cannot wait on each other
       std::lock_guard<std::mutex> reg(g_registry_mu);
-      for (agpu_device* other : g_registry) {
-        if (other == dev || other->ordinal != dev->ordinal) continue;
-        if (other->mu.try_lock()) {
-          release_cache(other);
-          other->mu.unlock();
-        }
-      }
+      for (agpu_device* other : g_registry)
+        if (other != dev && other->ordinal == dev->ordinal && !other->capturing) release_cache(other);
     }
     cudaDeviceSynchronize();  // the stream-ordered frees of every handle have to complete first
     e = cudaMallocAsync(out, want, dev->stream);
   }
   if (e != cudaSuccess) return (int)e;
-  dev->block_size[*out] = want;
+  g_blocks[*out] = Block{want, dev, false, dev->capturing, {}};
   return 0;
+}
+
+// order `waiter`'s stream behind everything `done` has enqueued so far
+static void order_after(agpu_device* waiter, agpu_device* done) {
+  if (waiter == done || waiter->capturing || done->capturing) return;
+  agpu_make_current(done);
+  if (cudaEventRecord(done->order_event, done->stream) == cudaSuccess) {
+    agpu_make_current(waiter);
+    cudaStreamWaitEvent(waiter->stream, done->order_event, 0);
+  }
 }
 
 extern "C" int agpu_free(agpu_device* dev, void* ptr) {
   if (!dev) return AGPU_ENODEVICE;
   if (!ptr) return 0;
-  std::lock_guard<std::mutex> lock(dev->mu);
-  auto it = dev->block_size.find(ptr);
-  if (it == dev->block_size.end()) {  // not one of ours (should not happen): plain stream-ordered free
-    AGPU_CUDA(cudaFreeAsync(ptr, dev->stream));
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  auto it = g_blocks.find(ptr);
+  if (it == g_blocks.end() || it->second.cached) return AGPU_EDOUBLEFREE;
+  Block& b = it->second;
+  if (!b.owner) {  // the allocating handle is gone: hand the block back to the driver, ordered on this stream
+    agpu_make_current(dev);
+    for (agpu_device* u : b.users) order_after(dev, u);
+    if (b.from_malloc) { cudaStreamSynchronize(dev->stream); cudaFree(ptr); }
+    else cudaFreeAsync(ptr, dev->stream);
+    g_blocks.erase(it);
     return 0;
   }
-  dev->free_blocks.emplace(it->second, ptr);
-  dev->cached_bytes += it->second;
+  agpu_device* owner = b.owner;
+  // the block may only be handed out again (on the owner's stream) after every other handle that
+  // read or wrote it has finished: the freeing handle, and the handles recorded as users
+  if (dev != owner) order_after(owner, dev);
+  for (agpu_device* u : b.users) order_after(owner, u);
+  b.users.clear();
+  if (owner->capturing) {  // a temporary of the graph being captured: it stays with the graph
+    owner->capture_freed.push_back(ptr);
+    return 0;
+  }
+  b.cached = true;
+  owner->free_blocks.emplace(b.size, ptr);
+  owner->cached_bytes += b.size;
+  return 0;
+}
+
+extern "C" int agpu_buffer_record_use(agpu_device* dev, const void* ptr) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!ptr) return 0;
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  auto it = g_blocks.find(const_cast<void*>(ptr));
+  if (it == g_blocks.end()) return 0;  // not pool memory (IPC / foreign allocation): nothing to guard
+  Block& b = it->second;
+  if (b.cached) return AGPU_EDOUBLEFREE;  // use after free
+  if (b.owner == dev) return 0;
+  for (agpu_device* u : b.users)
+    if (u == dev) return 0;
+  b.users.push_back(dev);
   return 0;
 }
 
 /* give every cached block back to the driver pool (e.g. before another library needs the memory) */
 extern "C" int agpu_trim(agpu_device* dev) {
   if (!dev) return AGPU_ENODEVICE;
-  std::lock_guard<std::mutex> lock(dev->mu);
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  agpu_make_current(dev);
   release_cache(dev);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one submit per recorded pipeline: stream capture -> CUDA graph (compute_pipeline.rs:259-273)
+// ---------------------------------------------------------------------------------------------
+extern "C" int agpu_graph_begin(agpu_device* dev) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (dev->capturing) return AGPU_EINVAL;
+  agpu_make_current(dev);
+  AGPU_CUDA(cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeThreadLocal));
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  dev->capturing = true;
+  dev->capture_launches0 = dev->launches;
+  dev->capture_freed.clear();
+  return 0;
+}
+
+static void return_blocks_to_cache(agpu_device* dev, std::vector<void*>& blocks) {  // caller holds g_mem_mu
+  for (void* p : blocks) {
+    auto it = g_blocks.find(p);
+    if (it == g_blocks.end()) continue;
+    Block& b = it->second;
+    agpu_device* owner = b.owner ? b.owner : dev;
+    b.owner = owner;
+    b.cached = true;
+    owner->free_blocks.emplace(b.size, p);
+    owner->cached_bytes += b.size;
+  }
+  blocks.clear();
+}
+
+extern "C" int agpu_graph_end(agpu_device* dev, agpu_graph** out) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!dev->capturing || !out) return AGPU_EINVAL;
+  *out = nullptr;
+  agpu_make_current(dev);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(dev->stream, &graph);
+  agpu_graph* g = new agpu_graph();
+  {
+    std::lock_guard<std::mutex> lock(g_mem_mu);
+    dev->capturing = false;
+    g->blocks.swap(dev->capture_freed);
+    g->kernels = dev->launches - dev->capture_launches0;
+    dev->launches = dev->capture_launches0;  // captured kernels have not run yet: counted per replay
+    if (e != cudaSuccess || !graph) return_blocks_to_cache(dev, g->blocks);
+  }
+  if (e != cudaSuccess || !graph) {
+    delete g;
+    cudaGetLastError();
+    return e != cudaSuccess ? (int)e : AGPU_EINVAL;
+  }
+  g->graph = graph;
+  g->dev = dev;
+  const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+  if (ie != cudaSuccess) {
+    cudaGraphDestroy(graph);
+    std::lock_guard<std::mutex> lock(g_mem_mu);
+    return_blocks_to_cache(dev, g->blocks);
+    delete g;
+    return (int)ie;
+  }
+  *out = g;
+  return 0;
+}
+
+extern "C" int agpu_graph_launch(agpu_device* dev, agpu_graph* g) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!g || !g->exec || g->dev != dev || dev->capturing) return AGPU_EINVAL;
+  agpu_make_current(dev);
+  AGPU_CUDA(cudaGraphLaunch(g->exec, dev->stream));
+  dev->launches += g->kernels;
+  return 0;
+}
+
+extern "C" uint64_t agpu_graph_kernel_count(agpu_graph* g) { return g ? g->kernels : 0; }
+
+extern "C" int agpu_graph_destroy(agpu_graph* g) {
+  if (!g) return 0;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  {
+    // replays were ordered on the handle's stream, and so is every later user of these blocks
+    std::lock_guard<std::mutex> lock(g_mem_mu);
+    bool alive = false;
+    {
+      std::lock_guard<std::mutex> reg(g_registry_mu);
+      for (agpu_device* d : g_registry) alive = alive || d == g->dev;
+    }
+    if (alive) return_blocks_to_cache(g->dev, g->blocks);
+  }
+  delete g;
   return 0;
 }
 
 extern "C" int agpu_h2d(agpu_device* dev, void* dst, const void* src, size_t bytes) {
   if (!dev) return AGPU_ENODEVICE;
+  if (dev->capturing) return AGPU_EINVAL;  // would read host memory / synchronise inside a stream capture
+  agpu_make_current(dev);
   if (bytes == 0) return 0;
   AGPU_REQUIRE(dst && src);
   AGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, dev->stream));
@@ -186,6 +357,8 @@ extern "C" int agpu_h2d(agpu_device* dev, void* dst, const void* src, size_t byt
 
 extern "C" int agpu_d2h(agpu_device* dev, void* dst, const void* src, size_t bytes) {
   if (!dev) return AGPU_ENODEVICE;
+  if (dev->capturing) return AGPU_EINVAL;  // would read host memory / synchronise inside a stream capture
+  agpu_make_current(dev);
   if (bytes) {
     AGPU_REQUIRE(dst && src);
     AGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream));
@@ -196,6 +369,7 @@ extern "C" int agpu_d2h(agpu_device* dev, void* dst, const void* src, size_t byt
 
 extern "C" int agpu_d2h_async(agpu_device* dev, void* dst, const void* src, size_t bytes) {
   if (!dev) return AGPU_ENODEVICE;
+  agpu_make_current(dev);
   if (bytes == 0) return 0;
   AGPU_REQUIRE(dst && src);
   AGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream));
@@ -204,6 +378,7 @@ extern "C" int agpu_d2h_async(agpu_device* dev, void* dst, const void* src, size
 
 extern "C" int agpu_d2d(agpu_device* dev, void* dst, const void* src, size_t bytes) {
   if (!dev) return AGPU_ENODEVICE;
+  agpu_make_current(dev);
   if (bytes == 0) return 0;
   AGPU_REQUIRE(dst && src);
   AGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, dev->stream));
@@ -212,6 +387,7 @@ extern "C" int agpu_d2d(agpu_device* dev, void* dst, const void* src, size_t byt
 
 extern "C" int agpu_memset(agpu_device* dev, void* dst, int byte_value, size_t bytes) {
   if (!dev) return AGPU_ENODEVICE;
+  agpu_make_current(dev);
   if (bytes == 0) return 0;
   AGPU_REQUIRE(dst);
   AGPU_CUDA(cudaMemsetAsync(dst, byte_value, bytes, dev->stream));
@@ -220,6 +396,8 @@ extern "C" int agpu_memset(agpu_device* dev, void* dst, int byte_value, size_t b
 
 extern "C" int agpu_sync(agpu_device* dev) {
   if (!dev) return AGPU_ENODEVICE;
+  if (dev->capturing) return AGPU_EINVAL;  // would read host memory / synchronise inside a stream capture
+  agpu_make_current(dev);
   AGPU_CUDA(cudaStreamSynchronize(dev->stream));
   return 0;
 }
@@ -254,6 +432,7 @@ extern "C" int agpu_event_destroy(agpu_event* ev) {
 
 extern "C" int agpu_event_record(agpu_device* dev, agpu_event* ev) {
   if (!dev) return AGPU_ENODEVICE;
+  agpu_make_current(dev);
   AGPU_REQUIRE(ev);
   AGPU_CUDA(cudaEventRecord(ev->ev, dev->stream));
   return 0;
@@ -261,6 +440,7 @@ extern "C" int agpu_event_record(agpu_device* dev, agpu_event* ev) {
 
 extern "C" int agpu_stream_wait_event(agpu_device* dev, agpu_event* ev) {
   if (!dev) return AGPU_ENODEVICE;
+  agpu_make_current(dev);
   AGPU_REQUIRE(ev);
   AGPU_CUDA(cudaStreamWaitEvent(dev->stream, ev->ev, 0));
   return 0;

@@ -30,6 +30,8 @@ template <class Op> struct IsJointOp<Op, std::void_t<decltype(Op::JOINT)>> : std
 
 template <class Op, int UNROLL, class Bm>
 __global__ void __launch_bounds__(kBlock) ew_kernel(const Op op, const size_t n, const Bm bm) {
+  pdl_wait();               // launched with programmatic stream serialization: see AGPU_LAUNCH_PDL
+  pdl_launch_dependents();  // the next kernel may start launching once every CTA of this grid is resident
   constexpr int G = Op::G;
   const size_t n_gran = n / G;
   const size_t tile_gran = (size_t)kBlock * UNROLL;
@@ -62,6 +64,8 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Op op, const size_t n,
 // Fallback for buffers that are not 16-byte aligned: one row per thread, same results.
 template <class Op, class Bm>
 __global__ void __launch_bounds__(kBlock) ew_kernel_unaligned(const Op op, const size_t n, const Bm bm) {
+  pdl_wait();
+  pdl_launch_dependents();
   const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
   if (i < n) op.tail(i);
   // 256 rows = 8 bitmap words per CTA (the host clears bm.vec for this kernel)
@@ -75,13 +79,13 @@ static int launch_ew(agpu_device* dev, const Op& op, size_t n, const Bm& bm, boo
     const size_t tile_rows = (size_t)kBlock * UNROLL * Op::G;
     const size_t grid = ceil_div(n, tile_rows);
     if (grid > 0x7FFFFFFFull) return AGPU_EINVAL;
-    AGPU_LAUNCH(dev, (ew_kernel<Op, UNROLL, Bm>), (unsigned)grid, kBlock, 0, op, n, bm);
+    AGPU_LAUNCH_PDL(dev, (ew_kernel<Op, UNROLL, Bm>), (unsigned)grid, kBlock, 0, op, n, bm);
   } else {
     const size_t grid = ceil_div(n, (size_t)kBlock);
     if (grid > 0x7FFFFFFFull) return AGPU_EINVAL;
     Bm scalar_bm = bm;
     scalar_bm.vec = 0;
-    AGPU_LAUNCH(dev, (ew_kernel_unaligned<Op, Bm>), (unsigned)grid, kBlock, 0, op, n, scalar_bm);
+    AGPU_LAUNCH_PDL(dev, (ew_kernel_unaligned<Op, Bm>), (unsigned)grid, kBlock, 0, op, n, scalar_bm);
   }
   return agpu_finish_launch();
 }

@@ -255,27 +255,38 @@ template <typename U>
 struct PutOp {
   static constexpr int G = 4;
   const U* src;
+  size_t src_len;
   const uint32_t* si;
   U* dst;
+  size_t dst_len;
   const uint32_t* di;
   struct In { Vec<uint32_t, 4> s, d; };
   __device__ __forceinline__ In load(size_t g) const { return In{ld_vec<uint32_t, 4>(si, g), ld_vec<uint32_t, 4>(di, g)}; }
+  // wgpu robust buffer access (which the reference's put.wgsl relies on): an out-of-range source
+  // index reads zero, an out-of-range destination index writes nothing
+  __device__ __forceinline__ U fetch(uint32_t s) const { return s < src_len ? src[s] : (U)0; }
   __device__ __forceinline__ void run(size_t, const In& in) const {
     U v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = src[in.s.e[k]];
+    for (int k = 0; k < 4; ++k) v[k] = fetch(in.s.e[k]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[in.d.e[k]] = v[k];
+    for (int k = 0; k < 4; ++k)
+      if (in.d.e[k] < dst_len) dst[in.d.e[k]] = v[k];
   }
-  __device__ __forceinline__ void tail(size_t j) const { dst[di[j]] = src[si[j]]; }
+  __device__ __forceinline__ void tail(size_t j) const {
+    const uint32_t d = di[j];
+    if (d < dst_len) dst[d] = fetch(si[j]);
+  }
 };
 
-__global__ void __launch_bounds__(kBlock) put_bits_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ si,
-                                                          uint32_t* dst, const uint32_t* __restrict__ di, const size_t m) {
+__global__ void __launch_bounds__(kBlock) put_bits_kernel(const uint32_t* __restrict__ src, const size_t src_len,
+                                                          const uint32_t* __restrict__ si, uint32_t* dst, const size_t dst_len,
+                                                          const uint32_t* __restrict__ di, const size_t m) {
   const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= m) return;  // (the reference lacks this bound: Q9)
   const uint32_t s = si[i], d = di[i];
-  const uint32_t bit = (src[s >> 5] >> (s & 31)) & 1u;
+  if (d >= dst_len) return;
+  const uint32_t bit = s < src_len ? (src[s >> 5] >> (s & 31)) & 1u : 0u;
   if (bit) atomicOr(dst + (d >> 5), 1u << (d & 31));
   else atomicAnd(dst + (d >> 5), ~(1u << (d & 31)));
 }
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
                                                                 const uint32_t* __restrict__ vmask, const size_t n,
                                                                 const uint32_t* __restrict__ counts,
                                                                 const uint64_t* __restrict__ group_offsets,
-                                                                U* __restrict__ out, uint32_t* vout) {
+                                                                U* __restrict__ out, uint32_t* vout, const uint64_t cap) {
   constexpr int G = 16 / sizeof(U);                   // rows per 16-byte granule
   constexpr int M = 4 / sizeof(U);                    // count-tiles per super tile
   constexpr int ROWS = kFilterTileRows * M;           // rows per super tile (16 KiB of rows)
@@ -526,9 +537,11 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
     if (lane == 31) count_s = incl;
   }
   __syncthreads();
-  const uint32_t count = count_s;
-  if (count == 0) return;  // uniform for the CTA
   const uint64_t off = off_s;
+  // rows past the capacity of the output buffers are dropped (a caller that sized the output from
+  // a selectivity estimate learns the real total from the count pass and retries)
+  const uint32_t count = off >= cap ? 0u : (uint32_t)min((uint64_t)count_s, cap - off);
+  if (count == 0) return;  // uniform for the CTA
   const bool vec_out = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
   const uint32_t lead = vec_out ? (uint32_t)(off % G) : 0u;  // shift so that 16-byte vectors line up
 
@@ -679,7 +692,7 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_tma_kernel(const U* __r
                                                                     const uint32_t* __restrict__ vmask, const size_t n,
                                                                     const uint32_t* __restrict__ counts,
                                                                     const uint64_t* __restrict__ group_offsets,
-                                                                    U* __restrict__ out, uint32_t* vout) {
+                                                                    U* __restrict__ out, uint32_t* vout, const uint64_t cap) {
   constexpr int G = 16 / sizeof(U);
   constexpr int GPT = kFilterTileRows / G / kBlock;
   constexpr uint32_t kTileBytes = kFilterTileRows * sizeof(U);
@@ -768,14 +781,15 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_tma_kernel(const U* __r
       if (lane == 31) sm.count = incl;
     }
     __syncthreads();
-    const uint32_t count = sm.count;
     const uint64_t off = sm.off;
+    const uint32_t count_all = sm.count;
+    const uint32_t count = off >= cap ? 0u : (uint32_t)min((uint64_t)count_all, cap - off);
     const uint32_t lead = vec_out ? (uint32_t)(off % G) : 0u;
     if (full) {  // every thread observes the completion of this buffer's bulk copy
       mbar_wait(&sm.bar[buf], buf ? parity1 : parity0);
       if (buf) parity1 ^= 1; else parity0 ^= 1;
     }
-    if (count) {
+    if (count_all) {
       const U* rows = sm.raw[buf];
 #pragma unroll
       for (int j = 0; j < GPT; ++j) {
@@ -792,7 +806,7 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_tma_kernel(const U* __r
         for (int k = 0; k < G; ++k) {
           if ((bits >> k) & 1u) {
             sm.stage[pos] = full ? v.e[k] : src[row0 + r + k];
-            if (HAS_V && ((vw >> k) & 1u)) atomicOr(&sm.vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
+            if (HAS_V && ((vw >> k) & 1u) && pos - lead < count) atomicOr(&sm.vstage[(pos - lead) >> 5], 1u << ((pos - lead) & 31));
             ++pos;
           }
         }
@@ -834,7 +848,7 @@ __global__ void __launch_bounds__(kBlock) filter_scatter_tma_kernel(const U* __r
 
 template <typename U, bool HAS_V>
 int launch_filter_tma(agpu_device* dev, const U* src, const uint32_t* vsrc, const uint32_t* mask, const uint32_t* vmask,
-                      size_t n, const FilterScratch& sc, U* out, uint32_t* vout) {
+                      size_t n, const FilterScratch& sc, U* out, uint32_t* vout, uint64_t cap) {
   const size_t tiles = filter_tiles(n);
   const int smem = (int)sizeof(FilterTmaSmem<U>) + 128;
   static bool configured = false;  // per instantiation
@@ -848,13 +862,13 @@ int launch_filter_tma(agpu_device* dev, const U* src, const uint32_t* vsrc, cons
   size_t grid = (size_t)dev->sm_count * per_sm;
   if (grid > tiles) grid = tiles;
   AGPU_LAUNCH(dev, (filter_scatter_tma_kernel<U, HAS_V>), (unsigned)grid, kBlock, smem, src, vsrc, mask, vmask, n, sc.counts,
-              sc.group_offsets, out, vout);
+              sc.group_offsets, out, vout, cap);
   return agpu_finish_launch();
 }
 
 template <typename U>
 int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const uint32_t* mask, const uint32_t* vmask,
-               size_t n, const FilterScratch& sc, void* out, uint32_t* vout) {
+               size_t n, const FilterScratch& sc, void* out, uint32_t* vout, size_t cap) {
   const size_t tiles = filter_tiles(n);
   if (tiles > 0x7FFFFFFFull) return AGPU_EINVAL;
   if (!aligned16(src)) return AGPU_EINVAL;  // tile bases must be 16-byte aligned
@@ -866,19 +880,20 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
   static const bool use_tma = getenv("AGPU_FILTER_TMA") != nullptr;
   if (use_tma) {
     if (vsrc && vout) {
-      AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
-      return launch_filter_tma<U, true>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout);
+      AGPU_CUDA(cudaMemsetAsync(vout, 0, ((cap + 31) / 32) * 4, dev->stream));
+      return launch_filter_tma<U, true>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout, cap);
     }
-    return launch_filter_tma<U, false>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout);
+    return launch_filter_tma<U, false>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout, cap);
   }
   // 512- and 1024-thread CTAs measured 10-50 % slower (profiles/r01_filter_variants.md)
   if (vsrc && vout) {
-    AGPU_CUDA(cudaMemsetAsync(vout, 0, ((n + 31) / 32) * 4, dev->stream));
+    // only the words the compacted rows can reach are cleared (the kernel ORs bit groups into them)
+    AGPU_CUDA(cudaMemsetAsync(vout, 0, ((cap + 31) / 32) * 4, dev->stream));
     AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
-                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
+                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
   } else {
     AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
-                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout);
+                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
   }
   return agpu_finish_launch();
 }
@@ -928,22 +943,23 @@ extern "C" int agpu_take(agpu_device* dev, int dtype, const void* src, size_t sr
   }
 }
 
-extern "C" int agpu_put(agpu_device* dev, int dtype, const void* src, const uint32_t* src_idx, void* dst,
-                        const uint32_t* dst_idx, size_t m) {
+extern "C" int agpu_put(agpu_device* dev, int dtype, const void* src, size_t src_len, const uint32_t* src_idx, void* dst,
+                        size_t dst_len, const uint32_t* dst_idx, size_t m) {
   if (!dev) return AGPU_ENODEVICE;
   if (m && (!src || !src_idx || !dst || !dst_idx)) return AGPU_EINVAL;
   if (m == 0) return 0;
   const unsigned grid = (unsigned)ceil_div(m, (size_t)kBlock);
   if (dtype == AGPU_BOOL) {
-    AGPU_LAUNCH(dev, put_bits_kernel, grid, kBlock, 0, (const uint32_t*)src, src_idx, (uint32_t*)dst, dst_idx, m);
+    AGPU_LAUNCH(dev, put_bits_kernel, grid, kBlock, 0, (const uint32_t*)src, src_len, src_idx, (uint32_t*)dst, dst_len,
+                dst_idx, m);
     return agpu_finish_launch();
   }
   BmAnd none{};
   const bool al = aligned16(src_idx) && aligned16(dst_idx);
   switch (agpu_dtype_size(dtype)) {
-    case 4: return launch_ew(dev, PutOp<uint32_t>{(const uint32_t*)src, src_idx, (uint32_t*)dst, dst_idx}, m, none, al);
-    case 2: return launch_ew(dev, PutOp<uint16_t>{(const uint16_t*)src, src_idx, (uint16_t*)dst, dst_idx}, m, none, al);
-    case 1: return launch_ew(dev, PutOp<uint8_t>{(const uint8_t*)src, src_idx, (uint8_t*)dst, dst_idx}, m, none, al);
+    case 4: return launch_ew(dev, PutOp<uint32_t>{(const uint32_t*)src, src_len, src_idx, (uint32_t*)dst, dst_len, dst_idx}, m, none, al);
+    case 2: return launch_ew(dev, PutOp<uint16_t>{(const uint16_t*)src, src_len, src_idx, (uint16_t*)dst, dst_len, dst_idx}, m, none, al);
+    case 1: return launch_ew(dev, PutOp<uint8_t>{(const uint8_t*)src, src_len, src_idx, (uint8_t*)dst, dst_len, dst_idx}, m, none, al);
     default: return AGPU_EUNSUPPORTED;
   }
 }
@@ -971,15 +987,16 @@ extern "C" int agpu_filter_count(agpu_device* dev, const uint32_t* mask, const u
 
 extern "C" int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src, const uint32_t* vsrc,
                                    const uint32_t* mask, const uint32_t* vmask, size_t n, void* scratch,
-                                   void* out, uint32_t* vout) {
+                                   void* out, uint32_t* vout, size_t out_capacity) {
   if (!dev) return AGPU_ENODEVICE;
-  if (n && (!src || !mask || !scratch || !out)) return AGPU_EINVAL;
-  if (n == 0) return 0;
+  if (n && (!src || !mask || !scratch)) return AGPU_EINVAL;
+  if (n == 0 || out_capacity == 0) return 0;
+  if (!out) return AGPU_EINVAL;
   const FilterScratch sc = filter_scratch(scratch, n);
   switch (agpu_dtype_size(dtype)) {
-    case 4: return run_filter<uint32_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
-    case 2: return run_filter<uint16_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
-    case 1: return run_filter<uint8_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout);
+    case 4: return run_filter<uint32_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout, out_capacity);
+    case 2: return run_filter<uint16_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout, out_capacity);
+    case 1: return run_filter<uint8_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout, out_capacity);
     default: return AGPU_EUNSUPPORTED;
   }
 }

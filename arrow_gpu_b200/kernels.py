@@ -32,6 +32,7 @@ def _eager(op_fn):
     """default_impl! of the reference: new pipeline -> *_op -> finish"""
     def run(self, *args):
         pipeline = _pipeline_for(self)
+        _note_foreign_buffers(self.gpu_device, (self,) + args)
         out = op_fn(self, *args, pipeline)
         pipeline.finish()
         return out
@@ -546,7 +547,7 @@ def _put_op(self, src_indexes, dst, dst_indexes, pipeline):
         raise NotImplementedError("put with validity bitmaps is todo!() in the reference (routines/src/lib.rs:164-169)")
     _check_same_len(src_indexes, dst_indexes, "put")
     dev = self.gpu_device
-    check(lib().agpu_put(dev.handle, self.DTYPE, self.data.ptr, src_indexes.data.ptr, dst.data.ptr,
+    check(lib().agpu_put(dev.handle, self.DTYPE, self.data.ptr, self.len, src_indexes.data.ptr, dst.data.ptr, dst.len,
                          dst_indexes.data.ptr, src_indexes.len), "put")
 
 
@@ -574,17 +575,19 @@ def _filter_count_op(self, mask, pipeline, total_ptr=None) -> FilterPlan:
 
 
 def _filter_scatter_op(self, plan: FilterPlan, count: int, pipeline):
-    """second half of filter: compact values (and validity) into a `count`-row array"""
+    """second half of filter: compact values (and validity) into a `count`-row array.  `count` may
+    be an upper bound on the selected rows (a sharded caller launches this before the exact total
+    has reached the host): buffers are sized for it, rows beyond it are dropped by the kernel."""
     dev = self.gpu_device
     mask = plan.mask
     out = type(self).empty(count, dev)
     vout = None
     if self.null_buffer is not None:
-        vout = dev.create_empty_buffer(bitmap_words(self.len) * 4 + 4)
+        vout = dev.create_empty_buffer(bitmap_words(count) * 4)
         out.null_buffer = NullBitBufferGpu(vout, count, dev)
     check(lib().agpu_filter_scatter(dev.handle, self.DTYPE, self.data.ptr, _vptr(self.null_buffer), mask.data.ptr,
                                     _vptr(mask.null_buffer), self.len, plan.scratch.ptr, out.data.ptr,
-                                    vout.ptr if vout else None), "filter_scatter")
+                                    vout.ptr if vout else None, count), "filter_scatter")
     return out
 
 
@@ -986,9 +989,33 @@ for _name, _fn in list(vars(PrimitiveArrayGpu).items()):
 # profiling hook (the reference's `profile` feature, gpu_utils/compute_query.rs): every `*_op`
 # recorded on a pipeline created with profile=True is bracketed by a CUDA event pair
 # ==========================================================================================
+def _note_foreign_buffers(dev, operands) -> None:
+    """ops run on `dev` (= self.gpu_device).  A column whose buffer was allocated through another
+    handle of the same GPU (uploaded on a copy stream, say) is recorded as used by `dev`, so that
+    dropping it cannot hand the block out again while this op still reads it."""
+    for x in operands:
+        if isinstance(x, PrimitiveArrayGpu):
+            buf, nb = x._data, x._null_buffer
+        elif isinstance(x, BooleanArrayGPU):
+            buf, nb = x.data, x.null_buffer
+        else:
+            continue
+        if buf is not None and buf.device is not dev and buf._kind == "pool" and buf._owned:
+            dev.record_use(buf)
+        if nb is not None and nb.bit_buffer.device is not dev and nb.bit_buffer._kind == "pool" and nb.bit_buffer._owned:
+            dev.record_use(nb.bit_buffer)
+
+
 def _profiled(name, fn):
+    in_place = name == "put_op"
+
     def wrapper(self, *args, **kwargs):
         pipeline = next((a for a in reversed(args) if isinstance(a, ArrowComputePipeline)), None)
+        _note_foreign_buffers(self.gpu_device, (self,) + args)
+        if in_place and pipeline is not None and pipeline._lazies:
+            # put_op mutates `dst` right away; chains recorded earlier on this pipeline that read it
+            # have to run first, as they do in the reference's encoder order
+            pipeline.flush_recorded()
         if pipeline is not None and pipeline.profile:
             start = pipeline.device.record_event()
             out = fn(self, *args, **kwargs)

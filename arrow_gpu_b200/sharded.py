@@ -87,45 +87,180 @@ def barrier() -> None:
 _EXCHANGE_CTX: dict = {}
 
 
-def sharded_filter(array, mask):
+class CountExchange:
+    """Device-side exchange of one u64 per rank between the GPUs of the box (agpu_exchange_post /
+    agpu_exchange_wait): every rank owns a slot area in IPC-exportable memory that all peers have
+    mapped; a post is one 8-byte store per peer over NVLink, a wait polls local memory.  No host
+    synchronisation and no collective-library call on the data path; torch.distributed is used
+    once, here, to hand the IPC handles around."""
+
+    def __init__(self, device):
+        import ctypes as C
+        from ._ffi import check, lib
+        from .array import ArrowGpuBuffer
+        dist = _dist()
+        self.device = device
+        self.rank = dist.get_rank() if dist else 0
+        self.world = dist.get_world_size() if dist else 1
+        nbytes = lib().agpu_exchange_bytes(self.world)
+        p = C.c_void_p()
+        check(lib().agpu_ipc_alloc(device.handle, nbytes, C.byref(p)), "agpu_ipc_alloc")
+        self.slots = ArrowGpuBuffer(device, p.value, nbytes, kind="ipc")
+        check(lib().agpu_memset(device.handle, self.slots.ptr, 0, nbytes), "agpu_memset")
+        device.sync()                       # zeroed before anybody can learn the handle
+        mine = device.ipc_export(self.slots)
+        handles = [mine]
+        if dist:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine)
+        self.peers = [self.slots if r == self.rank else device.ipc_open(h, nbytes) for r, h in enumerate(handles)]
+        self.ptrs = (C.c_void_p * self.world)(*[b.ptr for b in self.peers])
+        self.seq = 0
+        barrier()
+
+    def post(self, value_ptr: int) -> None:
+        """enqueue: store the u64 at device address `value_ptr` into every rank's slot area"""
+        from ._ffi import check, lib
+        check(lib().agpu_exchange_post(self.device.handle, value_ptr, self.ptrs, self.rank, self.world, self.seq),
+              "agpu_exchange_post")
+
+    def wait(self, out_ptr: int, timeout_ms: int = 10000) -> None:
+        """enqueue: wait on the GPU for all ranks' values of the current exchange and write
+        offsets / total / status / counts (2*world+2 u64) at device address `out_ptr`"""
+        from ._ffi import check, lib
+        check(lib().agpu_exchange_wait(self.device.handle, self.slots.ptr, self.world, self.seq, out_ptr, timeout_ms),
+              "agpu_exchange_wait")
+        self.seq += 1
+
+    def close(self) -> None:
+        barrier()
+        self.peers = []
+
+
+def count_exchange(device) -> CountExchange:
+    """the CountExchange of a device handle (created on first use; collective: every rank must call)"""
+    key = (id(device), "peer-exchange")
+    ctx = _EXCHANGE_CTX.get(key)
+    if ctx is None:
+        ctx = _EXCHANGE_CTX[key] = CountExchange(device)
+    return ctx
+
+
+def parse_exchange_result(words, rank: int, world: int):
+    """(offsets[world], total, counts[world]) from the 2*world+2 u64 agpu_exchange_wait writes"""
+    words = [int(w) for w in words]
+    if words[world + 1] != 0:
+        from ._ffi import AgpuError
+        raise AgpuError(-5, "agpu_exchange_wait")
+    return words[:world], words[world], words[world + 2: 2 * world + 2]
+
+
+class PendingShardedFilter:
+    """A sharded filter whose kernels are all enqueued: the compacted rows sit in `capacity`-row
+    buffers on the device, the counts of all shards are (or will be) on the device too.  Nothing
+    has synchronised with the host yet; `result()` does, once, and returns what `sharded_filter`
+    returns.  Dependent device work can be enqueued before calling it."""
+
+    def __init__(self, array, plan, out, capacity, info, info_kind, rank, world, gathered=None):
+        self.array, self.plan, self.out, self.capacity = array, plan, out, capacity
+        self.info, self.info_kind, self.rank, self.world, self.gathered = info, info_kind, rank, world, gathered
+        self._resolved = None
+
+    def result(self):
+        if self._resolved is not None:
+            return self._resolved
+        import numpy as np
+        from .array import NullBitBufferGpu
+        dev = self.array.gpu_device
+        if self.info_kind == "peer":
+            words = dev.retrive_data(self.info, (2 * self.world + 2) * 8).view(np.uint64)
+            offsets, total, counts = parse_exchange_result(words, self.rank, self.world)
+        elif self.info_kind == "nccl":
+            import torch
+            with torch.cuda.stream(self.info):
+                counts = self.gathered.cpu().tolist()      # one synchronisation, after everything was enqueued
+            offsets, total = exclusive_offsets(counts)
+        else:                                              # single shard: the count pass's total
+            counts = [int(dev.retrive_data(self.info, 8).view(np.uint64)[0])]
+            offsets, total = [0], counts[0]
+        count = int(counts[self.rank])
+        out = self.out
+        if count > self.capacity:      # the estimate was too small: redo the scatter with the exact size
+            out = self.array.filter_scatter_op(self.plan, count, None)
+        nb = None
+        if out.null_buffer is not None:
+            nb = NullBitBufferGpu(out.null_buffer.bit_buffer, count, dev)
+        final = type(out)(out.data, dev, count, nb)
+        self._resolved = (final, int(offsets[self.rank]), int(total))
+        self.plan = self.out = None
+        return self._resolved
+
+
+def sharded_filter_async(array, mask, capacity=None, exchange="peer") -> PendingShardedFilter:
+    """Enqueue a sharded filter without ANY host synchronisation:
+        count kernel -> post this shard's count to every peer -> scatter kernel -> wait for the peers
+    The output is sized for `capacity` rows (default: the shard's row count, always enough), so the
+    scatter never waits for the count to reach the host.  exchange: "peer" = one 8-byte store per
+    peer over NVLink + a polling kernel (CountExchange); "nccl" = all_gather_into_tensor on the same
+    stream (kept for comparison)."""
+    from .array import ArrowComputePipeline
+    dist = _dist()
+    dev = array.gpu_device
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    cap = array.len if capacity is None else min(int(capacity), array.len)
+    pipeline = ArrowComputePipeline(dev, "sharded_filter")
+    if dist is None or dist.get_backend() != "nccl":
+        plan = array.filter_count_op(mask, pipeline)
+        out = array.filter_scatter_op(plan, cap, pipeline)
+        pipeline.finish()
+        if dist is None:
+            return PendingShardedFilter(array, plan, out, cap, plan.total, "local", rank, world)
+        # CPU/gloo process groups (host-logic tests): counts travel through the host
+        import numpy as np
+        count = int(dev.retrive_data(plan.total, 8).view(np.uint64)[0])
+        offsets, total = exchange_counts(count)
+        pend = PendingShardedFilter(array, plan, out, cap, None, "host", rank, world)
+        pend._resolved = (type(out)(out.data, dev, count, out.null_buffer), offsets[rank], total)
+        return pend
+    if exchange == "peer":
+        ex = count_exchange(dev)
+        plan = array.filter_count_op(mask, pipeline)
+        ex.post(plan.total.ptr)
+        out = array.filter_scatter_op(plan, cap, pipeline)
+        info = dev.create_empty_buffer((2 * world + 2) * 8)
+        ex.wait(info.ptr)
+        pipeline.finish()
+        return PendingShardedFilter(array, plan, out, cap, info, "peer", rank, world)
+    import torch
+    ctx = _EXCHANGE_CTX.get(id(dev))
+    if ctx is None:   # per device handle: its stream as a torch stream
+        tdev = torch.device("cuda", dev.ordinal)
+        ctx = torch.cuda.ExternalStream(dev.stream_ptr, device=tdev)
+        torch.cuda.synchronize(tdev)
+        _EXCHANGE_CTX[id(dev)] = ctx
+    ext = ctx
+    with torch.cuda.stream(ext):
+        mine = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", dev.ordinal))
+        gathered = torch.zeros(world, dtype=torch.int64, device=mine.device)
+        plan = array.filter_count_op(mask, pipeline, total_ptr=mine.data_ptr())
+        dist.all_gather_into_tensor(gathered, mine)
+        out = array.filter_scatter_op(plan, cap, pipeline)
+        pipeline.finish()
+    pend = PendingShardedFilter(array, plan, out, cap, ext, "nccl", rank, world, gathered=gathered)
+    pend._keep = mine
+    return pend
+
+
+def sharded_filter(array, mask, capacity=None, exchange="peer"):
     """Filter this rank's shard and learn where its output sits in the global result:
     returns (local filtered array, global offset of its first row, global row count).
 
-    On GPUs (NCCL) the per-shard counts never leave the device before the exchange: the count
-    kernel writes this rank's total into a device word, `all_gather_into_tensor` runs on the SAME
-    stream (torch sees the library's stream as an ExternalStream), and one 8*world-byte readback
-    gives every rank all counts — a single host synchronisation per filter instead of one for the
-    local count plus one per gathered value."""
-    dist = _dist()
-    if dist is None or dist.get_backend() != "nccl":
-        out = array.filter(mask)
-        offsets, total = exchange_counts(out.len)
-        rank = dist.get_rank() if dist is not None else 0
-        return out, offsets[rank], total
-    import torch
-    from .array import ArrowComputePipeline
-    dev = array.gpu_device
-    rank, world = dist.get_rank(), dist.get_world_size()
-    ctx = _EXCHANGE_CTX.get(id(dev))
-    if ctx is None:   # per device handle: its stream as a torch stream + reusable count buffers
-        tdev = torch.device("cuda", dev.ordinal)
-        ctx = (torch.cuda.ExternalStream(dev.stream_ptr, device=tdev),
-               torch.zeros(1, dtype=torch.int64, device=tdev), torch.zeros(world, dtype=torch.int64, device=tdev),
-               torch.zeros(world, dtype=torch.int64).pin_memory())
-        torch.cuda.synchronize(tdev)
-        _EXCHANGE_CTX[id(dev)] = ctx
-    ext, mine, gathered, host = ctx
-    with torch.cuda.stream(ext):
-        pipeline = ArrowComputePipeline(dev, "sharded_filter")
-        plan = array.filter_count_op(mask, pipeline, total_ptr=mine.data_ptr())
-        dist.all_gather_into_tensor(gathered, mine)
-        host.copy_(gathered, non_blocking=True)
-        ext.synchronize()                         # the one synchronisation
-        counts = host.tolist()
-    offsets, total = exclusive_offsets(counts)
-    out = array.filter_scatter_op(plan, int(counts[rank]), pipeline)
-    pipeline.finish()
-    return out, offsets[rank], total
+    All kernels of the filter AND the count exchange are enqueued before the host looks at anything
+    (sharded_filter_async); the single synchronisation is the final read of the 8*(2*world+2)-byte
+    result block.  Round 1 synchronised between the count and the scatter pass (all_gather +
+    readback + stream sync), which left the GPU idle for a host round trip per filter."""
+    return sharded_filter_async(array, mask, capacity, exchange).result()
 
 
 # ------------------------------------------------------------------------------------------

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define AGPU_ABI_VERSION 1
+#define AGPU_ABI_VERSION 2
 
 /* dtype ids — crates/array/src/array/mod.rs:40-50 (enum ArrowType) */
 typedef enum {
@@ -93,13 +93,18 @@ typedef enum { AGPU_GT = 0, AGPU_GTEQ = 1, AGPU_LT = 2, AGPU_LTEQ = 3, AGPU_EQ =
 typedef enum { AGPU_SHL = 0, AGPU_SHR = 1 } agpu_shiftop;
 
 /* error codes (negative; positive values are cudaError_t) */
+#define AGPU_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
+#define AGPU_MAX_SHARDS 16       /* GPUs of one box a column can be sharded over */
 #define AGPU_OK 0
 #define AGPU_EUNSUPPORTED (-1) /* op/dtype pair the path does not define */
 #define AGPU_EINVAL (-2)       /* NULL where a pointer is required, bad size ... */
 #define AGPU_ENODEVICE (-3)    /* no CUDA device / device handle invalid */
+#define AGPU_EDOUBLEFREE (-4)  /* agpu_free of a block that is already free / was never allocated here */
+#define AGPU_ETIMEOUT (-5)     /* a peer GPU did not post its value (agpu_exchange_wait) */
 
 typedef struct agpu_device agpu_device; /* opaque: {ordinal, cudaStream_t, cudaMemPool_t} */
 typedef struct agpu_event agpu_event;   /* opaque cudaEvent_t wrapper */
+typedef struct agpu_graph agpu_graph;   /* opaque: a captured pipeline (cudaGraphExec_t + its temporaries) */
 
 /* ---- device / buffer layer: replaces GpuDevice (crates/array/src/gpu_utils/gpu_device.rs) ---- */
 
@@ -122,8 +127,18 @@ int agpu_abi_version(void);
  * stream that waits for it), and must be freed through the same handle. */
 int agpu_alloc(agpu_device* dev, size_t bytes, void** out);
 /* Drop of wgpu::Buffer — stream-ordered free, safe right after enqueueing work.  Freed blocks
- * are cached per handle and reused by later agpu_alloc calls of a similar size. */
+ * are cached by the handle that allocated them and reused by its later agpu_alloc calls of a
+ * similar size.  `dev` may be any handle of the same GPU: the block goes back to its owner, whose
+ * stream is first ordered behind `dev` and behind every handle recorded with
+ * agpu_buffer_record_use.  Freeing twice (or a pointer agpu_alloc never returned) fails with
+ * AGPU_EDOUBLEFREE and changes nothing. */
 int agpu_free(agpu_device* dev, void* ptr);
+/* wgpu keeps a buffer alive until every submitted command that uses it has finished
+ * (buffer.rs:5-7: Arc<wgpu::Buffer>).  With one stream per handle that is automatic for the
+ * allocating handle; when ANOTHER handle `dev` (e.g. the compute handle reading a column that an
+ * upload handle allocated) enqueues work on the block at `ptr`, it says so here, and agpu_free
+ * makes the owner wait for that handle before the block can be handed out again. */
+int agpu_buffer_record_use(agpu_device* dev, const void* ptr);
 /* return every cached free block to the driver */
 int agpu_trim(agpu_device* dev);
 /* create_gpu_buffer_with_data, gpu_device.rs:171-181 (host may be pageable or pinned) */
@@ -149,6 +164,21 @@ int agpu_event_elapsed_ms(agpu_event* start, agpu_event* stop, float* ms); /* wa
 /* make all later work of `dev` wait (on the GPU, not the host) for an event recorded on another
  * handle's stream: lets an upload stream run ahead of the compute stream */
 int agpu_stream_wait_event(agpu_device* dev, agpu_event* ev);
+
+/* ---- one submit per recorded pipeline ----
+ * ArrowComputePipeline records every op into one wgpu CommandEncoder and `finish()` submits the
+ * whole program at once (compute_pipeline.rs:259-273).  CUDA analogue: everything enqueued on the
+ * handle between agpu_graph_begin and agpu_graph_end is captured into a CUDA graph instead of
+ * running; agpu_graph_launch replays all of it with ONE driver call (programmatic dependent launch
+ * edges between the streaming kernels included).  Buffers allocated inside the capture keep their
+ * addresses: those still alive belong to the caller (the replay overwrites them), those freed
+ * inside the capture stay with the graph until agpu_graph_destroy.  Host-synchronising calls
+ * (agpu_d2h, agpu_sync) are not allowed while capturing. */
+int agpu_graph_begin(agpu_device* dev);
+int agpu_graph_end(agpu_device* dev, agpu_graph** out);
+int agpu_graph_launch(agpu_device* dev, agpu_graph* graph);
+uint64_t agpu_graph_kernel_count(agpu_graph* graph); /* kernels one replay launches */
+int agpu_graph_destroy(agpu_graph* graph);
 
 /* ---- validity bitmaps: NullBitBufferGpu (crates/array/src/array/null_bit_buffer.rs) ---- */
 
@@ -283,9 +313,11 @@ int agpu_take(agpu_device* dev, int dtype, const void* src, size_t src_len, cons
               void* out, size_t m, const uint32_t* vsrc, uint32_t* vout);
 
 /* Swizzle::put_op, routines/src/lib.rs:145-170, put.rs:9-56, bool/put.wgsl:
- * dst[dst_idx[i]] = src[src_idx[i]] in place, i < m (duplicate dst indices: any one wins). */
-int agpu_put(agpu_device* dev, int dtype, const void* src, const uint32_t* src_idx, void* dst,
-             const uint32_t* dst_idx, size_t m);
+ * dst[dst_idx[i]] = src[src_idx[i]] in place, i < m (duplicate dst indices: any one wins).
+ * The shader relies on wgpu's robust buffer access; same contract here: src_idx[i] >= src_len
+ * reads zero, dst_idx[i] >= dst_len writes nothing (lengths in rows; bits for AGPU_BOOL). */
+int agpu_put(agpu_device* dev, int dtype, const void* src, size_t src_len, const uint32_t* src_idx,
+             void* dst, size_t dst_len, const uint32_t* dst_idx, size_t m);
 
 /* filter / compaction (named by BASELINE.json config 5; not in the reference — SURVEY a18).
  * Keeps rows whose mask bit is 1 and (if vmask) whose mask is valid, order preserving.
@@ -296,13 +328,37 @@ int agpu_put(agpu_device* dev, int dtype, const void* src, const uint32_t* src_i
  *                        and the total into *total_dev (a device uint64)
  *   agpu_filter_scatter: uses the counts/offsets in `scratch` to compact the values into
  *                        out[0 .. total) and, when vsrc and vout are given, the validity bits
- *                        into vout (which must hold ceil(n/32) words; it is zeroed first). */
+ *                        into vout.  `out_capacity` = rows `out` can hold (and vout:
+ *                        ceil(out_capacity/32) words, zeroed here first); rows beyond it are
+ *                        dropped, so a caller may launch the scatter BEFORE it knows the total
+ *                        (out_capacity = n is always enough) and read the total later. */
 size_t agpu_filter_scratch_bytes(size_t n);
 int agpu_filter_count(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n,
                       void* scratch, uint64_t* total_dev);
 int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src, const uint32_t* vsrc,
                         const uint32_t* mask, const uint32_t* vmask, size_t n, void* scratch,
-                        void* out, uint32_t* vout);
+                        void* out, uint32_t* vout, size_t out_capacity);
+
+/* ---- count / offset exchange between the shards of one box, device side (north_star (4)) ----
+ * Every rank (one process per GPU) owns a slot area of agpu_exchange_bytes(world) bytes in
+ * agpu_ipc_alloc memory, zeroed once, exported with agpu_ipc_export and opened by every peer.
+ *   agpu_exchange_post: stores this rank's u64 `*value_dev` (< 2^40) into slot[rank] of EVERY
+ *                       rank's area, straight over NVLink peer memory.  peer_slots = HOST array of
+ *                       `world` device pointers (entry `rank` = the local area).
+ *   agpu_exchange_wait: waits ON THE GPU until all `world` values of exchange `seq` have arrived in
+ *                       the local area, then writes out_dev[0..world) = exclusive prefix sums
+ *                       (global offset of each rank's output), out_dev[world] = total,
+ *                       out_dev[world+1] = status (0 ok, 1 = timed out after timeout_ms; 0 -> 10 s)
+ *                       and out_dev[world+2 .. 2*world+2) = the raw per-rank values.
+ * Both only enqueue a one-warp kernel on the handle's stream: a sharded filter runs
+ * count -> post -> scatter -> wait with no host synchronisation.  `seq` counts the exchanges of
+ * this group (0, 1, 2, ...; same on every rank); every rank must post and wait each of them. */
+#define AGPU_EXCHANGE_RING 4
+size_t agpu_exchange_bytes(int world);
+int agpu_exchange_post(agpu_device* dev, const uint64_t* value_dev, void* const* peer_slots, int rank,
+                       int world, uint32_t seq);
+int agpu_exchange_wait(agpu_device* dev, const void* my_slots, int world, uint32_t seq,
+                       uint64_t* out_dev, uint32_t timeout_ms);
 
 /* ---- "next" rows ---- */
 
@@ -311,8 +367,6 @@ int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src, const uint
  * gather kernel reads them directly over NVLink/NVSwitch peer memory — no all-to-all of
  * requests and replies.  Exportable buffers come from cudaMalloc (pool memory cannot be
  * exported). */
-#define AGPU_IPC_HANDLE_BYTES 64
-#define AGPU_MAX_SHARDS 16
 int agpu_ipc_alloc(agpu_device* dev, size_t bytes, void** out);
 int agpu_ipc_free(agpu_device* dev, void* ptr);
 int agpu_ipc_export(agpu_device* dev, const void* ptr, unsigned char handle[AGPU_IPC_HANDLE_BYTES]);

@@ -41,15 +41,32 @@ def main():
     assert np.array_equal(a.gt(o).raw_values(), vals[b:e] > other[b:e])
     assert np.array_equal(a.merge(o, m).raw_values(), np.where(keep[b:e], vals[b:e], other[b:e]))
 
-    # filter: local compaction + count exchange -> global placement
-    out, offset, total = sharded.sharded_filter(a, m)
+    # filter: local compaction + count exchange -> global placement.  Both exchange paths: the
+    # device-side peer-slot exchange (default) and NCCL all_gather on the same stream
     sel = keep & kvalid
-    assert total == int(sel.sum()), (total, int(sel.sum()))
-    assert offset == int(sel[:b].sum()), (rank, offset)
     want = vals[sel]
-    got = out.raw_values()
-    assert np.array_equal(got, want[offset:offset + len(got)])
-    assert np.array_equal(out.null_buffer.flags(), valid[sel][offset:offset + len(got)])
+    for how in ("peer", "nccl"):
+        out, offset, total = sharded.sharded_filter(a, m, exchange=how)
+        assert total == int(sel.sum()), (how, total, int(sel.sum()))
+        assert offset == int(sel[:b].sum()), (how, rank, offset)
+        got = out.raw_values()
+        assert np.array_equal(got, want[offset:offset + len(got)]), how
+        assert np.array_equal(out.null_buffer.flags(), valid[sel][offset:offset + len(got)]), how
+    # many filters enqueued back to back before the host looks at any of them (exercises the slot
+    # ring of the exchange: every one must see its own counts), then resolved in order
+    masks, pend = [], []
+    for k in range(9):
+        kk = np.random.default_rng(500 + k).random(n) < (0.1 + 0.1 * k)
+        masks.append(kk)
+        pend.append(sharded.sharded_filter_async(a, ag.BooleanArrayGPU.from_numpy(kk[b:e], None, dev)))
+    for kk, p in zip(masks, pend):
+        o, off, tot = p.result()
+        assert tot == int(kk.sum()) and off == int(kk[:b].sum()), (rank, tot, off)
+        assert np.array_equal(o.raw_values(), vals[kk][off:off + o.len])
+    # an output capacity that is too small is detected from the exchanged count and redone
+    o, off, tot = sharded.sharded_filter(a, m, capacity=10)
+    assert tot == int(sel.sum()) and np.array_equal(o.raw_values(), want[off:off + o.len])
+    assert np.array_equal(o.null_buffer.flags(), valid[sel][off:off + o.len])
 
     # the global result reassembled from the shards (all_gather of the ragged pieces via padding)
     t = torch.zeros(n, dtype=torch.int32, device=f"cuda:{local}")

@@ -27,7 +27,7 @@ def test_library_exports_every_header_symbol(ffi):
         assert hasattr(lib, name), f"{name} is declared in include/agpu.h but not exported by libagpu.so"
     # and every declared function has a ctypes signature (so tests call it with checked types)
     assert sorted(ffi.SIGNATURES) == declared
-    assert lib.agpu_abi_version() == 1
+    assert lib.agpu_abi_version() == 2
 
 
 def test_enum_ids_match_header(ffi):

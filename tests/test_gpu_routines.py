@@ -149,13 +149,14 @@ def test_filter_large_properties(device):
 
 
 def test_sharded_filter_nccl(device):
-    """row-range shards + device-side NCCL count exchange, one rank per visible GPU (max 2; a
-    single GPU still exercises the NCCL path with world_size 1)"""
+    """row-range shards + device-side count exchange (peer slots over CUDA IPC, and NCCL), global
+    take over peer memory: one rank per VISIBLE GPU (a single GPU still runs every path with
+    world_size 1, including the IPC mapping of its own slots)"""
     import os
     import subprocess
     import sys
     import arrow_gpu_b200._ffi as ffi
-    world = min(2, ffi.device_count())
+    world = max(1, ffi.device_count())
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300),
