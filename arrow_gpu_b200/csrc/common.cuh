@@ -13,6 +13,11 @@
 
 struct agpu_graph;
 
+struct PendingBlock {  // a freed block that other handles' streams have not got past yet (device.cu)
+  void* ptr;
+  std::vector<cudaEvent_t> events;
+};
+
 struct agpu_device {
   int ordinal;
   cudaStream_t stream;
@@ -23,12 +28,14 @@ struct agpu_device {
   // a fresh output (like the reference), so freed blocks are kept by size and handed out again
   // without going back to the driver pool — whose remapping when block sizes alternate costs
   // milliseconds (measured: profiles/r01_size_sweep.md).  Reuse is safe because a block only
-  // re-enters its OWNER's cache after the owner's stream has been ordered behind every other
-  // handle that used it (agpu_buffer_record_use + the event wait in agpu_free).
+  // re-enters its OWNER's cache after every other handle that used it (agpu_buffer_record_use)
+  // has got past that work: agpu_free records one event per such handle and parks the block in
+  // `pending` until they have all completed.
   // All allocator state of all handles is guarded by one global mutex (device.cu: g_mem_mu).
   std::multimap<size_t, void*> free_blocks;  // size -> cached block
   size_t cached_bytes = 0;
-  cudaEvent_t order_event = nullptr;         // "this stream's position now", for cross-handle ordering
+  std::vector<PendingBlock> pending;         // freed, but still in use on another handle's stream
+  cudaEvent_t order_event = nullptr;         // spare event of the handle
   // stream capture (agpu_graph_begin .. agpu_graph_end): blocks freed while capturing stay with the
   // graph (its kernels write them at every replay), they do not go back to the cache
   bool capturing = false;

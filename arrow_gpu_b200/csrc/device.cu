@@ -16,10 +16,11 @@ extern "C" int agpu_abi_version(void) { return AGPU_ABI_VERSION; }
 struct Block {
   size_t size;
   agpu_device* owner;                // the handle whose cache the block returns to (nullptr: owner destroyed)
-  bool cached;                       // sitting in owner->free_blocks
+  bool cached;                       // freed: sitting in owner->free_blocks or in owner->pending
   bool from_malloc;                  // cudaMalloc (allocated during a stream capture) instead of the pool
   std::vector<agpu_device*> users;   // other handles that enqueued work on it (agpu_buffer_record_use)
 };
+static std::vector<cudaEvent_t> g_event_pool;    // recycled "position of a stream" events (guarded by g_mem_mu)
 static std::mutex g_mem_mu;                      // guards g_blocks and every handle's free_blocks
 static std::unordered_map<void*, Block> g_blocks;  // every block handed out or cached
 static std::mutex g_registry_mu;
@@ -132,7 +133,10 @@ static void release_block(agpu_device* dev, void* ptr, const Block& b) {
   else cudaFreeAsync(ptr, dev->stream);
 }
 
+static void process_pending(agpu_device* dev, bool wait);
+
 static void release_cache(agpu_device* dev) {  // caller holds g_mem_mu
+  process_pending(dev, true);
   for (auto& kv : dev->free_blocks) {
     auto it = g_blocks.find(kv.second);
     if (it != g_blocks.end()) {
@@ -160,6 +164,7 @@ extern "C" int agpu_alloc(agpu_device* dev, size_t bytes, void** out) {
   *out = nullptr;
   const size_t want = round_block(bytes);
   std::lock_guard<std::mutex> lock(g_mem_mu);
+  process_pending(dev, false);
   // best fit among cached blocks, but never waste more than 25 % (+1 MiB) of a block
   auto it = dev->free_blocks.lower_bound(want);
   if (it != dev->free_blocks.end() && it->first <= want + want / 4 + (1u << 20)) {
@@ -187,14 +192,45 @@ extern "C" int agpu_alloc(agpu_device* dev, size_t bytes, void** out) {
   return 0;
 }
 
-// order `waiter`'s stream behind everything `done` has enqueued so far
-static void order_after(agpu_device* waiter, agpu_device* done) {
-  if (waiter == done || waiter->capturing || done->capturing) return;
-  agpu_make_current(done);
-  if (cudaEventRecord(done->order_event, done->stream) == cudaSuccess) {
-    agpu_make_current(waiter);
-    cudaStreamWaitEvent(waiter->stream, done->order_event, 0);
+static cudaEvent_t take_event() {  // caller holds g_mem_mu
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
   }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+
+// Blocks that other handles were still using when they were freed sit in owner->pending, each with
+// one event per such handle (its stream position at the time of the free).  They enter the cache —
+// and can be handed out again — only once all those events have completed.  Nothing waits: neither
+// the host nor any stream (same idea as record_stream in torch's caching allocator).
+static void process_pending(agpu_device* dev, bool wait) {  // caller holds g_mem_mu
+  if (dev->pending.empty() || dev->capturing) return;
+  size_t keep = 0;
+  for (size_t k = 0; k < dev->pending.size(); ++k) {
+    PendingBlock& p = dev->pending[k];
+    bool done = true;
+    for (cudaEvent_t e : p.events) {
+      if (wait) cudaEventSynchronize(e);
+      else if (cudaEventQuery(e) != cudaSuccess) { done = false; break; }
+    }
+    if (!done) {
+      cudaGetLastError();  // cudaErrorNotReady is sticky-free but shows up in cudaPeekAtLastError
+      if (keep != k) dev->pending[keep] = std::move(p);
+      ++keep;
+      continue;
+    }
+    for (cudaEvent_t e : p.events) g_event_pool.push_back(e);
+    auto it = g_blocks.find(p.ptr);
+    if (it != g_blocks.end()) {
+      dev->free_blocks.emplace(it->second.size, p.ptr);
+      dev->cached_bytes += it->second.size;
+    }
+  }
+  dev->pending.resize(keep);
 }
 
 extern "C" int agpu_free(agpu_device* dev, void* ptr) {
@@ -204,27 +240,44 @@ extern "C" int agpu_free(agpu_device* dev, void* ptr) {
   auto it = g_blocks.find(ptr);
   if (it == g_blocks.end() || it->second.cached) return AGPU_EDOUBLEFREE;
   Block& b = it->second;
-  if (!b.owner) {  // the allocating handle is gone: hand the block back to the driver, ordered on this stream
+  if (!b.owner) {  // the allocating handle is gone: hand the block back to the driver once every user is done
+    for (agpu_device* u : b.users) cudaStreamSynchronize(u->stream);
     agpu_make_current(dev);
-    for (agpu_device* u : b.users) order_after(dev, u);
     if (b.from_malloc) { cudaStreamSynchronize(dev->stream); cudaFree(ptr); }
     else cudaFreeAsync(ptr, dev->stream);
     g_blocks.erase(it);
     return 0;
   }
   agpu_device* owner = b.owner;
-  // the block may only be handed out again (on the owner's stream) after every other handle that
-  // read or wrote it has finished: the freeing handle, and the handles recorded as users
-  if (dev != owner) order_after(owner, dev);
-  for (agpu_device* u : b.users) order_after(owner, u);
-  b.users.clear();
   if (owner->capturing) {  // a temporary of the graph being captured: it stays with the graph
+    b.users.clear();
     owner->capture_freed.push_back(ptr);
     return 0;
   }
+  // the block may only be handed out again (on the owner's stream) after every OTHER handle that
+  // read or wrote it has got past the work it had enqueued: the freeing handle and the recorded users
+  if (dev != owner) {
+    bool known = false;
+    for (agpu_device* u : b.users) known = known || u == dev;
+    if (!known) b.users.push_back(dev);
+  }
   b.cached = true;
-  owner->free_blocks.emplace(b.size, ptr);
-  owner->cached_bytes += b.size;
+  if (b.users.empty()) {
+    owner->free_blocks.emplace(b.size, ptr);
+    owner->cached_bytes += b.size;
+  } else {
+    PendingBlock p;
+    p.ptr = ptr;
+    for (agpu_device* u : b.users) {
+      if (u->capturing) continue;
+      agpu_make_current(u);
+      cudaEvent_t e = take_event();
+      if (e && cudaEventRecord(e, u->stream) == cudaSuccess) p.events.push_back(e);
+    }
+    b.users.clear();
+    owner->pending.push_back(std::move(p));
+  }
+  process_pending(owner, false);
   return 0;
 }
 

@@ -668,6 +668,7 @@ def fused_mul_add_gt_op(a, b, c, d, pipeline) -> BooleanArrayGPU:
             raise Panic(f"fused_mul_add_gt not supported for type {x.get_dtype()}")
         _check_same_len(a, x, "fused_mul_add_gt")
     dev = a.gpu_device
+    _note_foreign_buffers(dev, (a, b, c, d))
     nb = _new_validity(dev, a.len, a.null_buffer, b.null_buffer, c.null_buffer, d.null_buffer)
     out = BooleanArrayGPU.empty(a.len, dev, nb)
     check(lib().agpu_fused_mul_add_gt(dev.handle, a.data.ptr, b.data.ptr, c.data.ptr, d.data.ptr, out.data.ptr,
@@ -749,6 +750,7 @@ def fused_chain_op(data, steps, pipeline):
         else:
             raise Panic(f"fused_chain: operand of {name!r} must be a Float32ArrayGPU or a number")
     dev = data.gpu_device
+    _note_foreign_buffers(dev, [data] + [st[1] for st in steps if len(st) > 1 and isinstance(st[1], PrimitiveArrayGpu)])
     nb = _new_validity(dev, data.len, *validities)
     out = (BooleanArrayGPU if is_pred else Float32ArrayGPU).empty(data.len, dev, nb)
     check(lib().agpu_fused_chain(dev.handle, data.DTYPE, data.data.ptr, _vptr(data.null_buffer), arr, len(steps),
@@ -829,6 +831,7 @@ def fused_chain_int_op(data, steps, pipeline):
             arr[k].kind, arr[k].operand, arr[k].validity = kinds[0], operand.data.ptr, _vptr(operand.null_buffer)
             validities.append(operand.null_buffer)
     dev = data.gpu_device
+    _note_foreign_buffers(dev, [data] + [st[1] for st in steps if len(st) > 1 and isinstance(st[1], PrimitiveArrayGpu)])
     nb = _new_validity(dev, data.len, *validities)
     out = (BooleanArrayGPU if is_pred else type(data)).empty(data.len, dev, nb)
     check(lib().agpu_fused_chain_int(dev.handle, data.DTYPE, data.data.ptr, _vptr(data.null_buffer), arr, len(steps),

@@ -4,23 +4,36 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (default, N=1): BASELINE.json configs[1] — "i8/u8/i16/u16 arithmetic, logical and cast
-across types, 256M rows, 1 B200" with the op list of SURVEY.md §8(d) cfg 2.  One STEP = one pass
-of all 55 ops over their 268 435 456-row synthetic columns.  `value` = row-operations per second
-(ops x rows / device time) with inputs resident in HBM; `e2e` = the same step through the public
-array API from pinned HOST buffers (H2D of every input column, D2H of every output column inside
-the timed region); `roofline` = algorithmic bytes of the slowest op / its CUDA-event time against
-the measured HBM copy peak; `cpu_baseline` = the oracle port (OpenMP) on a bounded sample.
-N > 1: weak scaling — every rank runs the same step on its own row-range shard, no collective on
-the data path (element-wise ops shard with zero communication), time = max over ranks.
+Headline workload (`value`, N = 1): BASELINE.json configs[1] — "i8/u8/i16/u16 arithmetic, logical
+and cast across types, 256M rows, 1 B200" with the op list of SURVEY.md §8(d) cfg 2.  One STEP =
+one pass of all 55 ops over their 268 435 456-row synthetic columns.
+  value      row-operations per second (ops x rows / device time), inputs resident in HBM, the K
+             steps launched back to back (no events inside the timed region)
+  per_op     the same ops timed one by one with CUDA events on the launching stream
+  roofline   the op FURTHEST BELOW the HBM roofline (lowest algorithmic GB/s / measured copy peak)
+  e2e        the same step through the public array API from pinned HOST buffers: H2D of every
+             input column on an upload stream, D2H of every output column on a download stream
+  parity     every one of the 55 full-size outputs compared bit for bit with the oracle's output on
+             the same host columns (non-timed); a mismatch fails the run (exit code 1)
+  cpu_baseline  the oracle port (OpenMP) on the host cores, rank 0, full columns
+  per_config the OTHER BASELINE.json configs, each with its own per-op table, clocks window,
+             cpu_baseline, parity on a bounded sample and (cfg 1, 3, 5-filter) e2e:
+             cfg1 (1 Mi rows f32 add + gt with nulls; eager and as ONE captured submit), cfg3 (fused
+             (a*b+c)>d, 1 G rows) — N = 1 only; cfg4 (f32 sqrt/exp/sin/cos over 4 G rows, row-range
+             sharded: strong scaling) and cfg5 (merge / filter with the device-side count exchange /
+             take on 4 G int32 rows, sharded; `collective_us` per exchange) at every N.
+N > 1: cfg 2 is weak-scaled — every rank runs the same step on its own row-range shard, no
+collective on the data path, time = max over ranks.
 
 `--impl reference` times the reference's CPU stand-in (oracle/, the C restatement of its shaders;
 the reference itself is Rust+WGSL on wgpu/lavapipe and cannot be built in this image) on the host
-cores for the same config/metric.  oracle/ is imported ONLY in that arm and in the cpu_baseline leg.
+cores for the same config/metric.  oracle/ is imported ONLY in that arm, in the cpu_baseline legs
+and in the parity checks.
 """
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -37,6 +50,15 @@ ROWS_CFG2 = 268_435_456
 SIZES = {"i8": 1, "u8": 1, "i16": 2, "u16": 2, "i32": 4, "u32": 4, "f32": 4}
 NPT = {"i8": np.int8, "u8": np.uint8, "i16": np.int16, "u16": np.uint16, "i32": np.int32, "u32": np.uint32,
        "f32": np.float32}
+METRIC = "rows/s (row-operations per second over the 55 ops of config 2; achieved HBM GB/s per op in per_op)"
+DTYPE = "u8/i8/u16/i16 (+u32 shift counts, f32 for casts)"
+
+
+def config_dict(rows: int):
+    """the SAME dict in both arms (the driver compares them)"""
+    return {"workload": "BASELINE.json configs[1]: i8/u8/i16/u16 arithmetic, logical, shift and cast, "
+                        f"{rows} rows per GPU, 55 ops per step", "rows_per_gpu": rows, "ops_per_step": 55,
+            "l2": "inputs larger than L2 (every column >= 256 MiB vs 126 MB L2)", "sharding": "row-range, no collective"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -60,25 +82,47 @@ def cfg2_ops():
     return ops
 
 
+def pinned_by_reference(spec) -> bool:
+    """False for the ops BASELINE.json config 2 names but the reference does not implement
+    (sub-word + - x, array and scalar; only `u16 + scalar` exists: arithmetic/compute_shaders/u16/
+    scalar.wgsl:15-23).  For those the oracle is the definition — parity unpinned."""
+    label, kind, _t, op, _d = spec
+    if kind == "binary" and op in ("add", "sub", "mul"):
+        return False
+    if kind == "scalar":
+        return label == "u16.add_scalar"
+    return True
+
+
 def bytes_per_row(spec) -> float:
     _label, kind, t, _op, d = spec
     es, ds = SIZES[t], SIZES[d]
     return {"binary": 3 * es, "scalar": 2 * es, "unary": 2 * es, "shift": 2 * es + 4, "cast": es + ds}[kind]
 
 
-def cfg2_columns(rows: int, seed0: int = 10):
+def cfg2_columns(rows: int, seed0: int = 10, out=None):
     """synthetic columns of SURVEY.md §8(d) cfg 2: full-range uniform ints (seed 10+k), shift
-    counts U{0..width-1}, f32 U(-10, 70000) for the narrowing cast"""
+    counts U{0..width-1}, f32 U(-10, 70000) for the narrowing cast.  `out(name, n, dtype)` may
+    provide the destination arrays (pinned host memory)."""
     cols = {}
+
+    def put(name, values):
+        if out is None:
+            cols[name] = values
+        else:
+            dst = out(name, len(values), values.dtype)
+            dst[:] = values
+            cols[name] = dst
+
     for k, t in enumerate(("i8", "u8", "i16", "u16")):
         info = np.iinfo(NPT[t])
         rng = np.random.default_rng(seed0 + k)
-        cols[f"{t}.a"] = rng.integers(info.min, int(info.max) + 1, rows, dtype=NPT[t])
-        cols[f"{t}.b"] = rng.integers(info.min, int(info.max) + 1, rows, dtype=NPT[t])
+        put(f"{t}.a", rng.integers(info.min, int(info.max) + 1, rows, dtype=NPT[t]))
+        put(f"{t}.b", rng.integers(info.min, int(info.max) + 1, rows, dtype=NPT[t]))
     rng = np.random.default_rng(seed0 + 8)
-    cols["cnt8"] = rng.integers(0, 8, rows, dtype=np.uint32)
-    cols["cnt16"] = rng.integers(0, 16, rows, dtype=np.uint32)
-    cols["f32.a"] = rng.uniform(-10, 70000, rows).astype(np.float32)
+    put("cnt8", rng.integers(0, 8, rows, dtype=np.uint32))
+    put("cnt16", rng.integers(0, 16, rows, dtype=np.uint32))
+    put("f32.a", rng.uniform(-10, 70000, rows).astype(np.float32))
     return cols
 
 
@@ -114,42 +158,58 @@ def gpu_runner():
     return ag, cls, run
 
 
-def sample_clocks_start(index: int):
-    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-    try:
-        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-    except OSError:
-        return None
+class ClockSampler:
+    """ONE nvidia-smi process for the whole run (the recipe's clocks line, B200_PROFILING.md, plus
+    a timestamp column), 50 ms period; `window(t0, t1)` summarises the samples taken between two
+    time.time() marks, so every config gets the clocks seen during ITS timed region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-
-def sample_clocks_stop(proc):
-    if proc is None:
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    proc.terminate()
-    try:
-        out, _ = proc.communicate(timeout=10)
-    except subprocess.TimeoutExpired:
-        proc.kill()
-        out, _ = proc.communicate()
-    sm, mx, reasons = [], [], set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for line in out.splitlines():
-        f = [x.strip() for x in line.split(",")]
-        if len(f) < 9:
-            continue
+    def __init__(self, index: int):
+        self.samples = None
         try:
-            sm.append(float(f[1]))
-            mx.append(float(f[2]))
-        except ValueError:
-            continue
-        for name, val in zip(names, f[5:9]):
-            if val.lower().startswith("active"):
-                reasons.add(name)
-    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-            "samples": len(sm), "reasons": sorted(reasons)}
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.samples is not None:
+            return
+        self.samples = []
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=10)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 10:
+                continue
+            try:
+                t = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                sm, mx = float(f[2]), float(f[3])
+            except ValueError:
+                continue
+            self.samples.append((t, sm, mx, [n for n, v in zip(self.NAMES, f[6:10]) if v.lower().startswith("active")]))
+
+    def window(self, t0: float, t1: float):
+        self.stop()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside and self.samples:   # a window shorter than the sampling period: the nearest sample
+            mid = 0.5 * (t0 + t1)
+            inside = [min(self.samples, key=lambda s: abs(s[0] - mid))]
+        reasons = sorted({r for s in inside for r in s[3]})
+        return {"sm_mhz": statistics.median(s[1] for s in inside) if inside else None,
+                "sm_max_mhz": max((s[2] for s in inside), default=None), "samples": len(inside), "reasons": reasons,
+                "window_s": round(t1 - t0, 3)}
 
 
 def measured_peak():
@@ -167,24 +227,105 @@ def known_traffic(label: str):
     return None
 
 
-def run_ours(args, rank, world, local_rank):
+class NumaBinding:
+    """`with numa.bound():` pins the calling thread to the CPUs next to this rank's GPU while pinned
+    staging buffers are allocated (first touch places their pages on that NUMA node, so the PCIe
+    traffic of the 8 ranks does not cross the socket interconnect); everything else — the launch
+    loop, the OpenMP CPU legs — runs with the process's full affinity."""
+
+    def __init__(self, index: int):
+        self.full = os.sched_getaffinity(0)
+        self.cpus, self.info = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & self.full
+            if cpus and cpus != self.full:
+                self.cpus = cpus
+                self.info = {"bound": True, "cpus": len(cpus), "of": len(self.full)}
+            else:
+                self.info = {"bound": False, "cpus": len(self.full), "why": "GPU-local CPU set == process affinity"}
+        except Exception as e:  # noqa: BLE001 — NVML absent / not permitted: run unbound, say so
+            self.info = {"bound": False, "why": f"{type(e).__name__}: {e}"[:120]}
+
+    def bound(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            if self.cpus:
+                os.sched_setaffinity(0, self.cpus)
+            try:
+                yield
+            finally:
+                if self.cpus:
+                    os.sched_setaffinity(0, self.full)
+        return ctx()
+
+
+class Events:
+    def __init__(self, dev, lib, ffi):
+        import ctypes as C
+        self.C, self.dev, self.lib, self.ffi = C, dev, lib, ffi
+
+    def new(self):
+        e = self.C.c_void_p()
+        self.ffi.check(self.lib.agpu_event_create(self.C.byref(e)), "event_create")
+        return e
+
+    def record(self, e, dev=None):
+        self.ffi.check(self.lib.agpu_event_record((dev or self.dev).handle, e), "event_record")
+
+    def ms(self, a, b):
+        out = self.C.c_float(0)
+        self.ffi.check(self.lib.agpu_event_elapsed_ms(a, b, self.C.byref(out)), "event_elapsed")
+        return out.value
+
+
+def link_ceiling_probe(dev, up, down, lib, ffi, sharded, h2d_bytes, d2h_bytes, src_pinned, dst_pinned, dev_buf):
+    """What the host <-> device links give ALL ranks at once with plain cudaMemcpyAsync from/to pinned
+    memory and nothing else running: the e2e step's own byte counts in both directions, H2D and
+    D2H concurrently on two streams.  e2e cannot beat this; `link_frac` says how close it gets."""
+    chunk = min(len(src_pinned), len(dst_pinned), dev_buf.size)
+
+    def once():
+        sent = 0
+        while sent < h2d_bytes:
+            n = min(chunk, h2d_bytes - sent)
+            ffi.check(lib.agpu_h2d(up.handle, dev_buf.ptr, src_pinned.ctypes.data, n), "h2d")
+            sent += n
+        got = 0
+        while got < d2h_bytes:
+            n = min(chunk, d2h_bytes - got)
+            ffi.check(lib.agpu_d2h_async(down.handle, dst_pinned.ctypes.data, dev_buf.ptr, n), "d2h")
+            got += n
+        up.sync()
+        down.sync()
+
+    once()
+    sharded.barrier()
+    t0 = time.perf_counter()
+    once()
+    ms = sharded.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    return ms
+
+
+def run_ours(args, rank, world, local_rank, sampler, numa):
     import ctypes as C
     from arrow_gpu_b200 import _ffi, sharded
     ag, cls, run = gpu_runner()
     dev = ag.GpuDevice(local_rank)
     lib = _ffi.lib()
+    ev = Events(dev, lib, _ffi)
     rows = args.rows
     ops = cfg2_ops()
-    host = cfg2_columns(rows, seed0=10 + 100 * rank)
 
-    # pinned host staging: inputs (copied every e2e step) and one output landing buffer
-    pinned = {}
-    for name, arr in host.items():
-        p = dev.pinned_empty(len(arr), arr.dtype)
-        p[:] = arr
-        pinned[name] = p
-    del host
-    out_stage = dev.pinned_empty(rows * 4, np.uint8)
+    # pinned host staging: inputs (copied every e2e step) and two output landing buffers
+    with numa.bound():
+        pinned = cfg2_columns(rows, seed0=10 + 100 * rank, out=lambda _name, n, dt: dev.pinned_empty(n, dt))
+        landing = [dev.pinned_empty(rows * 4, np.uint8) for _ in range(2)]
 
     col_cls = {"cnt8": cls["u32"], "cnt16": cls["u32"]}
 
@@ -195,80 +336,76 @@ def run_ours(args, rank, world, local_rank):
     arrs = {name: upload(name, True) for name in pinned}
     scalars = {t: cls[t].from_slice([3], dev) for t in ("i8", "u8", "i16", "u16")}
 
-    def new_event():
-        e = C.c_void_p()
-        _ffi.check(lib.agpu_event_create(C.byref(e)), "event_create")
-        return e
-
-    def record(e):
-        _ffi.check(lib.agpu_event_record(dev.handle, e), "event_record")
-
-    def elapsed(a, b):
-        ms = C.c_float(0)
-        _ffi.check(lib.agpu_event_elapsed_ms(a, b, C.byref(ms)), "event_elapsed")
-        return ms.value
-
-    # ---- resident-input throughput (`value`) with per-op CUDA events on the launching stream ----
+    # ---- resident-input throughput (`value`): K steps back to back, nothing but kernels in the
+    # timed region (consecutive streaming kernels overlap tail and ramp: programmatic dependent launch)
     def resident_step(events=None):
         for k, spec in enumerate(ops):
             out = run(spec, arrs, scalars)
             del out  # stream-ordered free: the pool hands the block to the next op
             if events is not None:
-                record(events[k + 1])
+                ev.record(events[k + 1])
 
-    # the sampler runs from the warm-up on (same load as the timed steps): the timed region of
-    # K=5 steps lasts ~50 ms, shorter than nvidia-smi's sampling period
-    clocks_proc = sample_clocks_start(local_rank)
-    for _ in range(max(args.warmup, 1) * 8):
+    t_window0 = time.time()
+    for _ in range(args.warmup):
         resident_step()
     dev.sync()
     sharded.barrier()
-    step_events = [[new_event() for _ in range(len(ops) + 1)] for _ in range(args.steps)]
     launches0 = dev.launch_count()
-    t_start, t_stop = new_event(), new_event()
+    t_start, t_stop = ev.new(), ev.new()
     dev.sync()
-    record(t_start)
-    for s in range(args.steps):
-        record(step_events[s][0])
-        resident_step(step_events[s])
-    record(t_stop)
+    ev.record(t_start)
+    for _ in range(args.steps):
+        resident_step()
+    ev.record(t_stop)
     dev.sync()
     launches = dev.launch_count() - launches0
-    total_ms = elapsed(t_start, t_stop)
-    clocks = sample_clocks_stop(clocks_proc)
+    total_ms = ev.ms(t_start, t_stop)
     sharded.barrier()
     total_ms = sharded.max_over_ranks(total_ms)
 
-    per_op_ms = [statistics.mean(elapsed(step_events[s][k], step_events[s][k + 1]) for s in range(args.steps))
+    # ---- the same ops one by one (CUDA events between them: no overlap across ops)
+    step_events = [[ev.new() for _ in range(len(ops) + 1)] for _ in range(args.steps)]
+    for s in range(args.steps):
+        ev.record(step_events[s][0])
+        resident_step(step_events[s])
+    dev.sync()
+    t_window1 = time.time()
+    per_op_ms = [statistics.mean(ev.ms(step_events[s][k], step_events[s][k + 1]) for s in range(args.steps))
                  for k in range(len(ops))]
     peak, peak_src = measured_peak()
     per_op = {}
     for spec, ms in zip(ops, per_op_ms):
+        ms = sharded.max_over_ranks(ms)
         gbs = bytes_per_row(spec) * rows / (ms * 1e-3) / 1e9
         per_op[spec[0]] = {"ms": round(ms, 4), "rows_per_s": rows / (ms * 1e-3), "GBps": round(gbs, 1),
                            "B_per_row": bytes_per_row(spec), "frac_measured_peak": round(gbs / peak, 4),
-                           "frac_8TBps": round(gbs / 8000.0, 4)}
-    # dominant kernel = the op family that takes the largest share of the step
-    worst = max(range(len(ops)), key=lambda k: per_op_ms[k])
-    wl = ops[worst][0]
+                           "frac_8TBps": round(gbs / 8000.0, 4), "pinned": pinned_by_reference(spec)}
+    # the roofline line names the op FURTHEST BELOW the roofline, not the one that moves most bytes
+    wl = min(per_op, key=lambda k: per_op[k]["frac_measured_peak"])
+    step_bytes = sum(bytes_per_row(s) for s in ops) * rows
     roof = {"bound": "hbm", "kernel": wl, "achieved": per_op[wl]["GBps"], "peak": peak, "unit": "GB/s",
-            "frac": round(per_op[wl]["GBps"] / peak, 4), "traffic": known_traffic(wl), "peak_source": peak_src,
-            "share_of_step": round(per_op_ms[worst] / sum(per_op_ms), 4),
-            "step_mean_frac": round(sum(bytes_per_row(s) for s in ops) * rows / (sum(per_op_ms) * 1e-3) / 1e9 / peak, 4)}
+            "frac": per_op[wl]["frac_measured_peak"], "traffic": known_traffic(wl), "peak_source": peak_src,
+            "share_of_step": round(per_op[wl]["ms"] / sum(v["ms"] for v in per_op.values()), 4),
+            "step_mean_frac": round(step_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak, 4),
+            "step_mean_frac_one_by_one": round(step_bytes / (sum(v["ms"] for v in per_op.values()) * 1e-3) / 1e9 / peak, 4),
+            "below_target": sorted(k for k, v in per_op.items() if v["frac_8TBps"] < 0.80),
+            "target": ">= 0.80 of 8 TB/s per op (BASELINE.json north_star); the measured copy peak itself is "
+                      f"{peak / 8000:.3f} of 8 TB/s"}
     row_ops = len(ops) * rows * args.steps
     value = row_ops * world / (total_ms * 1e-3)
 
     # ---- end to end through the public API from pinned host buffers ----
-    # A second device handle (= a second stream on the same GPU) uploads the input columns while
-    # the compute handle works; each op waits on the GPU for the upload events of its inputs.
-    # Outputs are read back on the compute stream into a pinned landing buffer.  PCIe is full
-    # duplex, so H2D hides behind the (larger) D2H traffic.
-    up = ag.GpuDevice(local_rank)
+    # Three handles = three streams on the GPU: `up` uploads the input columns, `dev` computes (each
+    # op waits on the GPU for the upload events of its inputs), `down` copies every result column to
+    # one of two pinned landing buffers.  PCIe is full duplex; the allocator keeps a block that
+    # another stream still uses out of circulation until that stream is done (agpu_buffer_record_use).
+    up, down = ag.GpuDevice(local_rank), ag.GpuDevice(local_rank)
     order = []
     for spec in ops:
         for c in inputs_of(spec):
             if c not in order:
                 order.append(c)
+    done_ev = [ag.GpuEvent() for _ in ops]
 
     def e2e_step(read_back=True):
         live, ready = {}, {}
@@ -281,18 +418,22 @@ def run_ours(args, rank, world, local_rank):
         h2d = sum(a.nbytes for a in pinned.values())
         d2h = 0
         waited = set()
-        for spec in ops:
+        for k, spec in enumerate(ops):
             for c in inputs_of(spec):
                 if c not in waited:
                     dev.wait_event(ready[c])
                     waited.add(c)
             out = run(spec, live, scalars)
             if read_back:
-                view = out_stage[: out.len * out.NP.itemsize].view(out.NP)
-                out.raw_values(out=view, wait=False)
-                d2h += view.nbytes
+                nbytes = out.len * out.NP.itemsize
+                dev.record_event(done_ev[k])
+                down.wait_event(done_ev[k])
+                down.record_use(out.data)
+                _ffi.check(lib.agpu_d2h_async(down.handle, landing[k & 1].ctypes.data, out.data.ptr, nbytes), "d2h")
+                d2h += nbytes
         dev.sync()
         up.sync()
+        down.sync()
         return h2d, d2h
 
     e2e = None
@@ -301,36 +442,73 @@ def run_ours(args, rank, world, local_rank):
         sharded.barrier()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         t0 = time.perf_counter()
-        ev0, ev1 = new_event(), new_event()
-        record(ev0)
         for _ in range(e2e_steps):
             h2d, d2h = e2e_step()
-        record(ev1)
-        dev.sync()
-        e2e_ms = sharded.max_over_ranks(max(elapsed(ev0, ev1), (time.perf_counter() - t0) * 1e3))
+        e2e_ms = sharded.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        step_ms = e2e_ms / e2e_steps
         e2e = {"value": len(ops) * rows * e2e_steps * world / (e2e_ms * 1e-3), "unit": "rows/s", "steps": e2e_steps,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms / e2e_steps, 3),
-               "pcie_GBps": {"h2d": round(h2d / (e2e_ms / e2e_steps * 1e-3) / 1e9, 1),
-                             "d2h": round(d2h / (e2e_ms / e2e_steps * 1e-3) / 1e9, 1)}}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(step_ms, 3),
+               "pcie_GBps": {"h2d": round(h2d / (step_ms * 1e-3) / 1e9, 1), "d2h": round(d2h / (step_ms * 1e-3) / 1e9, 1)},
+               "streams": "upload / compute / download on three handles, two landing buffers"}
         # where the e2e time goes: the same step with the 55 result columns left on the device
-        # (uploads + compute only) — not the headline, it shows that e2e is the D2H link's time
         t0 = time.perf_counter()
         e2e_step(read_back=False)
-        e2e["upload_and_compute_only_ms_per_step"] = round(
-            sharded.max_over_ranks((time.perf_counter() - t0) * 1e3), 3)
+        e2e["upload_and_compute_only_ms_per_step"] = round(sharded.max_over_ranks((time.perf_counter() - t0) * 1e3), 3)
+        # and what the links give all ranks at once for these byte counts with nothing else going on
+        scratch = dev.create_empty_buffer(rows * 4)
+        probe_ms = link_ceiling_probe(dev, up, down, lib, _ffi, sharded, h2d, d2h, pinned["cnt8"].view(np.uint8),
+                                      landing[0], scratch)
+        del scratch
+        e2e["link_probe_ms_per_step"] = round(probe_ms, 3)
+        e2e["link_GBps_ceiling"] = {"h2d": round(h2d / (probe_ms * 1e-3) / 1e9, 1), "d2h": round(d2h / (probe_ms * 1e-3) / 1e9, 1),
+                                    "how": "plain cudaMemcpyAsync, pinned, H2D and D2H concurrently, all ranks at once, "
+                                           "the e2e step's byte counts"}
+        e2e["link_frac"] = round(probe_ms / step_ms, 4)
+
+    # ---- full-size parity: each of the 55 outputs vs the oracle on the same host columns ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_pass(ops, run, arrs, scalars, pinned, landing[0], rows, world)
+        parity["mismatches"] = int(sharded.sum_over_ranks(parity["mismatches"]))
+        parity["ranks_checked"] = world
+        parity["unpinned_ops"] = sorted(s[0] for s in ops if not pinned_by_reference(s))
 
     run_ours.host_columns = pinned     # reused by the cpu_baseline leg (same synthetic columns)
+    run_ours.handles = (dev, up, down)
+    run_ours.landing = landing
     result = {
-        "metric": "rows/s (row-operations per second over the 55 ops of config 2; achieved HBM GB/s per op in per_op)",
-        "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8/i8/u16/i16 (+u32 shift counts, f32 for casts)", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: i8/u8/i16/u16 arithmetic, logical, shift and cast, "
-                               f"{rows} rows per GPU, 55 ops per step", "rows_per_gpu": rows, "ops_per_step": len(ops),
-                   "l2": "inputs larger than L2 (every column >= 256 MiB vs 126 MB L2)", "sharding": "row-range, no collective"},
-        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "per_op": per_op,
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": config_dict(rows),
+        "gpu_launches": int(launches), "clocks": None, "e2e": e2e, "roofline": roof, "parity": parity, "per_op": per_op,
     }
+    run_ours.clock_window = (t_window0, t_window1)
     return result
+
+
+def parity_pass(ops, run, arrs, scalars, host_cols, landing, rows, world):
+    """GPU output of every op (resident inputs = uploads of `host_cols`) vs the oracle on `host_cols`."""
+    O, cpu_run = cpu_runner()
+    O.set_num_threads(max(1, len(os.sched_getaffinity(0)) // world))   # every rank checks its own shard at once
+    outs = {t: np.empty(rows, dtype=NPT[t]) for t in ("i8", "u8", "i16", "u16", "i32", "u32", "f32")}
+    bad_ops, mismatches = {}, 0
+    t0 = time.perf_counter()
+    for spec in ops:
+        got_dev = run(spec, arrs, scalars)
+        view = landing[: got_dev.len * got_dev.NP.itemsize].view(got_dev.NP)
+        got_dev.raw_values(out=view, wait=True)
+        want = cpu_run(spec, host_cols, outs)
+        # bit patterns (f32 results of the int -> f32 casts are exact, so NaN never occurs)
+        a = view.view(np.uint8)
+        b = want.view(np.uint8)
+        if not np.array_equal(a, b):
+            wrong = int(np.count_nonzero(view.view(f"u{view.dtype.itemsize}") != want.view(f"u{want.dtype.itemsize}")))
+            bad_ops[spec[0]] = wrong
+            mismatches += wrong
+        del got_dev
+    return {"ops": len(ops), "rows": rows, "mismatches": mismatches, "bad_ops": bad_ops,
+            "seconds": round(time.perf_counter() - t0, 1),
+            "how": "bit-exact compare of every full-size output column (D2H) with oracle/oracle.c on the same host columns"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -421,14 +599,10 @@ def run_reference(args, rank):
         return None
     base = time_cpu(args.cpu_rows, args.steps, args.warmup)
     return {
-        "impl": "reference",
-        "metric": "rows/s (row-operations per second over the 55 ops of config 2; achieved HBM GB/s per op in per_op)",
+        "impl": "reference", "metric": METRIC,
         "value": base["value"], "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/i8/u16/i16 (+u32 shift counts, f32 for casts)", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: i8/u8/i16/u16 arithmetic, logical, shift and cast, "
-                               f"bounded sample of {args.cpu_rows} rows per step, 55 ops per step",
-                   "ops_per_step": 55},
+        "dtype": DTYPE, "data": "synthetic", "config": config_dict(args.rows),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -442,13 +616,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=None, help="rows (default: the workload's own size; cfg2: 256 Mi per GPU)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "sweep", "allops"],
-                    help="BASELINE.json configs[k-1]; cfg2 is the bench line, the others are scaling/parity configs")
-    ap.add_argument("--cpu-rows", type=int, default=ROWS_CFG2,
-                    help="rows of the CPU sample (default: the full 256 Mi-row columns — a step is 1-4 s of CPU work on "
-                         "16-24 host threads, and a sample that fits the host's last-level cache would flatter the CPU)")
+                    help="BASELINE.json configs[k-1]; cfg2 is the bench line (with the others in per_config); naming "
+                         "another one runs only that config (profiling)")
+    ap.add_argument("--cpu-rows", type=int, default=None,
+                    help="rows of the CPU sample (default: the full columns — a step is 1-4 s of CPU work on 16-32 host "
+                         "threads, and a sample that fits the host's last-level cache would flatter the CPU)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true")
+    ap.add_argument("--per-config-scale", type=float, default=1.0,
+                    help="shrink the per_config row counts (smoke runs on small GPUs); 1.0 = BASELINE.json sizes")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version
     # banner there) are sent to stderr, the result goes to the saved descriptor
@@ -462,6 +641,9 @@ def main():
     args.rows_given = args.rows is not None
     if args.rows is None:
         args.rows = ROWS_CFG2
+    if args.cpu_rows is None:
+        args.cpu_rows = args.rows
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup   # timing rule: W >= 3
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -471,36 +653,72 @@ def main():
         res = run_reference(args, rank)
         if res is not None:
             emit(res)
-        return
+        return 0
 
+    numa = NumaBinding(local_rank)
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rc = 0
+    sampler = ClockSampler(local_rank)
+    helpers = {"sampler": sampler, "peak": measured_peak, "traffic": known_traffic, "numa": numa}
     try:
         if args.workload != "cfg2":
             import bench_workloads
-            res = bench_workloads.run(args, rank, world, local_rank,
-                                      {"clocks_start": sample_clocks_start, "clocks_stop": sample_clocks_stop,
-                                       "peak": measured_peak, "traffic": known_traffic})
+            res = bench_workloads.run(args, rank, world, local_rank, helpers)
             if rank == 0:
                 emit(res)
-            return
-        res = run_ours(args, rank, world, local_rank)
+            return 0
+        from arrow_gpu_b200 import sharded
+        res = run_ours(args, rank, world, local_rank, sampler, numa)
+        res["host_numa"] = numa.info
+        cpu = None
+        if not args.no_cpu_baseline:
+            sharded.barrier()
+            if rank == 0:   # the other ranks idle at the barrier below: the CPU leg has the host to itself
+                cpu = time_cpu(min(args.cpu_rows, args.rows), 3, 1, cols=run_ours.host_columns)
+                cpu["arrow_cross_check"] = time_arrow_cpu(run_ours.host_columns, min(1 << 24, args.rows))
+            sharded.barrier()
+        # free config 2 before the other configs take the GPU
+        dev = run_ours.handles[0]
+        for name in list(run_ours.host_columns):
+            dev.pinned_free(run_ours.host_columns.pop(name))
+        for buf in run_ours.landing:
+            dev.pinned_free(buf)
+        run_ours.landing = []
+        import gc
+        gc.collect()
+        per_config = None
+        if not args.no_per_config:
+            import bench_workloads
+            per_config = bench_workloads.per_config(args, rank, world, local_rank, helpers, run_ours.handles)
+        sampler.stop()
+        res["clocks"] = sampler.window(*run_ours.clock_window)
+        res["clocks"]["window"] = "warm-up + timed steps + per-op pass of config 2"
+        if per_config is not None:
+            for name, block in per_config.items():
+                if isinstance(block, dict) and "_window" in block:
+                    block["clocks"] = sampler.window(*block.pop("_window"))
+        res["per_config"] = per_config
+        res["cpu_baseline"] = cpu
+        bad = (res.get("parity") or {}).get("mismatches", 0)
+        for block in (per_config or {}).values():
+            if isinstance(block, dict):
+                bad += (block.get("parity") or {}).get("mismatches", 0)
+        if bad:
+            res["parity_failed"] = True
+            rc = 1
         if rank == 0:
-            if not args.no_cpu_baseline and world == 1:
-                res["cpu_baseline"] = time_cpu(min(args.cpu_rows, args.rows), 3, 1, cols=run_ours.host_columns)
-                res["cpu_baseline"]["arrow_cross_check"] = time_arrow_cpu(run_ours.host_columns,
-                                                                          min(1 << 24, args.rows))
-            else:
-                res["cpu_baseline"] = None
             emit(res)
     finally:
+        sampler.stop()
         if world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
+    return rc
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

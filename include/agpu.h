@@ -128,16 +128,17 @@ int agpu_abi_version(void);
 int agpu_alloc(agpu_device* dev, size_t bytes, void** out);
 /* Drop of wgpu::Buffer — stream-ordered free, safe right after enqueueing work.  Freed blocks
  * are cached by the handle that allocated them and reused by its later agpu_alloc calls of a
- * similar size.  `dev` may be any handle of the same GPU: the block goes back to its owner, whose
- * stream is first ordered behind `dev` and behind every handle recorded with
- * agpu_buffer_record_use.  Freeing twice (or a pointer agpu_alloc never returned) fails with
+ * similar size.  `dev` may be any handle of the same GPU: the block goes back to its owner, but
+ * only after `dev` and every handle recorded with agpu_buffer_record_use have got past the work
+ * they had enqueued at this moment (one event per handle; nothing waits, the block is just not
+ * handed out before).  Freeing twice (or a pointer agpu_alloc never returned) fails with
  * AGPU_EDOUBLEFREE and changes nothing. */
 int agpu_free(agpu_device* dev, void* ptr);
 /* wgpu keeps a buffer alive until every submitted command that uses it has finished
  * (buffer.rs:5-7: Arc<wgpu::Buffer>).  With one stream per handle that is automatic for the
  * allocating handle; when ANOTHER handle `dev` (e.g. the compute handle reading a column that an
- * upload handle allocated) enqueues work on the block at `ptr`, it says so here, and agpu_free
- * makes the owner wait for that handle before the block can be handed out again. */
+ * upload handle allocated) enqueues work on the block at `ptr`, it says so here, and after
+ * agpu_free the block is not handed out again before that handle's stream got there. */
 int agpu_buffer_record_use(agpu_device* dev, const void* ptr);
 /* return every cached free block to the driver */
 int agpu_trim(agpu_device* dev);

@@ -637,14 +637,15 @@ int oracle_compare(int op, int dtype, const void* a, const void* b, uint32_t* ou
  * shifts (count = one u32 per row)
  *   {i32,u32}/shift.wgsl:13-23; {i16,u16}/shift.wgsl (halves, i16 `shr` helper :31-41);
  *   {i8,u8}/shift.wgsl:13-45 (unpack4x -> vec4 shift -> pack4x)
- * WGSL takes the count modulo 32 on the 32-bit widened lane.  The i16 `shr` helper equals an
- * arithmetic shift of the sign-extended half for counts 0..15 (pinned by the reference's
- * vectors); for counts >= 16 its `16u - shift_value` underflows and parity is unpinned — the
- * arithmetic-shift value is used there.
+ * WGSL takes the count modulo 32 on the 32-bit widened lane.  The i16 `shr` helper is evaluated
+ * literally for EVERY count: its `16u - shift_value` wraps for counts > 16 and the shifts take
+ * their counts modulo 32 like any other WGSL shift.  (Counts 0..15 are pinned by the reference's
+ * vectors; for the rest the helper still equals the arithmetic shift of the sign-extended half by
+ * `count & 31` — tests/test_oracle_properties.py checks that over the whole range — but no
+ * reference vector covers it: SURVEY.md Q17.)
  * ---------------------------------------------------------------------------------------- */
 static inline int32_t i16_shr_helper(int32_t input, uint32_t shift_value) {
   /* logical/compute_shaders/i16/shift.wgsl:31-41 */
-  if (shift_value >= 16u) return i32_shr(input, shift_value); /* unpinned range */
   if (input < 0) {
     int32_t result = i32_shr(input, shift_value);
     int32_t other = i32_shl(0xffff, 16u - shift_value);

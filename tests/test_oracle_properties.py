@@ -142,3 +142,16 @@ def test_casts_and_sums(n, seed):
     assert int(np.asarray(O.sum(O.I32, i32)).astype(np.int64)) == int(((int(i32.astype(np.int64).sum()) + 2**31) % 2**32) - 2**31)
     small = rng.integers(-1000, 1000, n).astype(np.float32)                 # exactly representable partial sums
     assert float(np.asarray(O.sum(O.F32, small))) == float(small.astype(np.float64).sum())
+
+
+def test_i16_shr_helper_is_an_arithmetic_shift_for_every_count():
+    """logical/compute_shaders/i16/shift.wgsl:31-41 evaluated literally (the oracle does) equals
+    `lo16(sx(a) >> (count & 31))` for ALL counts, also where `16u - shift_value` wraps — so the
+    kernel's formula and the shader agree beyond the pinned 0..15 range."""
+    vals = np.array([-32768, -32767, -12345, -2, -1, 0, 1, 2, 12345, 32767], dtype=np.int16)
+    counts = np.array(list(range(0, 70)) + [255, 256, 2**31, 2**32 - 1], dtype=np.uint32)
+    a = np.repeat(vals, len(counts))
+    c = np.tile(counts, len(vals))
+    got = O.shift(O.SHR, O.I16, a, c)
+    want = (a.astype(np.int32) >> (c & 31).astype(np.int32)).astype(np.int16)
+    assert np.array_equal(got, want)
