@@ -74,6 +74,12 @@ class ArrowGpuBuffer {  // array/buffer.rs:5-7 — owns one stream-ordered alloc
   ~ArrowGpuBuffer() { if (ptr_) agpu_free(dev_->handle(), ptr_); }
   ArrowGpuBuffer(const ArrowGpuBuffer&) = delete;
   void* ptr() const { return ptr_; }
+  // the pointer, for work about to be enqueued on ANOTHER handle of the same GPU: the allocator
+  // then keeps the block out of circulation after Drop until that handle's stream got there
+  void* ptr_on(const DevicePtr& user) const {
+    if (user.get() != dev_.get()) check(agpu_buffer_record_use(user->handle(), ptr_), "record_use");
+    return ptr_;
+  }
   uint64_t size() const { return size_; }
   const DevicePtr& device() const { return dev_; }
   static std::shared_ptr<ArrowGpuBuffer> with_data(const DevicePtr& dev, const void* host, size_t bytes) {
@@ -99,14 +105,44 @@ class ArrowGpuBuffer {  // array/buffer.rs:5-7 — owns one stream-ordered alloc
 };
 using BufferPtr = std::shared_ptr<ArrowGpuBuffer>;
 
-class ArrowComputePipeline {  // gpu_utils/compute_pipeline.rs:8-22: a stream scope here
+// gpu_utils/compute_pipeline.rs:8-22.  By default a stream scope: every *_op enqueues at once and
+// finish() has nothing left to submit.  With capture = true it is the literal record-then-submit
+// object of the reference: ops recorded between construction and finish() are captured into a CUDA
+// graph (agpu_graph_begin/end), finish() submits the whole program with one driver call
+// (compute_pipeline.rs:259-273) and replay() submits the same recorded program again.
+class ArrowComputePipeline {
  public:
-  explicit ArrowComputePipeline(DevicePtr device, const char* label = nullptr) : device(std::move(device)), label_(label ? label : "") {}
-  void finish() { finished_ = true; }  // never waits, like the reference
+  explicit ArrowComputePipeline(DevicePtr device, const char* label = nullptr, bool capture = false)
+      : device(std::move(device)), label_(label ? label : ""), capture_(capture) {
+    if (capture_) check(agpu_graph_begin(this->device->handle()), "ArrowComputePipeline::new (capture)");
+  }
+  ArrowComputePipeline(const ArrowComputePipeline&) = delete;
+  ~ArrowComputePipeline() {
+    if (capture_ && !finished_) {  // abandoned recording: close the capture, submit nothing
+      agpu_graph* g = nullptr;
+      if (agpu_graph_end(device->handle(), &g) == 0 && g) agpu_graph_destroy(g);
+    }
+    if (graph_) agpu_graph_destroy(graph_);
+  }
+  void finish() {  // never waits, like the reference
+    if (capture_ && !finished_) {
+      finished_ = true;
+      check(agpu_graph_end(device->handle(), &graph_), "ArrowComputePipeline::finish (capture)");
+      replay();
+    }
+    finished_ = true;
+  }
+  void replay() {
+    if (!graph_) throw Panic("replay() needs a pipeline created with capture = true and finished");
+    check(agpu_graph_launch(device->handle(), graph_), "ArrowComputePipeline::replay");
+  }
+  uint64_t kernels_per_submit() const { return agpu_graph_kernel_count(graph_); }
   DevicePtr device;
  private:
   std::string label_;
+  bool capture_ = false;
   bool finished_ = false;
+  agpu_graph* graph_ = nullptr;
 };
 
 // ---------------------------------------------------------------- bitmaps

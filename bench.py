@@ -159,26 +159,63 @@ def gpu_runner():
 
 
 class ClockSampler:
-    """ONE nvidia-smi process for the whole run (the recipe's clocks line, B200_PROFILING.md, plus
-    a timestamp column), 50 ms period; `window(t0, t1)` summarises the samples taken between two
-    time.time() marks, so every config gets the clocks seen during ITS timed region."""
+    """SM clock and clock-event (throttle) reasons sampled for the WHOLE run, every 20 ms, through
+    NVML — the library behind the recipe's `nvidia-smi --query-gpu=clocks.sm,...` line
+    (B200_PROFILING.md); a pipe to an nvidia-smi child loses its last block-buffered samples when
+    the child is killed, and a 100 ms period misses millisecond-long configs.  `window(t0, t1)`
+    summarises the samples between two time.time() marks, so every config reports the clocks seen
+    during ITS timed region.  Falls back to one nvidia-smi child (line-buffered, 50 ms)."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.samples = None
+    def __init__(self, index: int, period_s: float = 0.02):
+        import threading
+        self.samples, self.proc, self.thread, self.source = [], None, None, None
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn(h)
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        r = int(reasons_fn(h))
+                        self.samples.append((time.time(), sm, mx, [n for n, b in bits.items() if r & b]))
+                    except Exception:  # noqa: BLE001
+                        pass
+                    self._stop.wait(period_s)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = f"NVML (pynvml), every {int(period_s * 1e3)} ms"
+        except Exception:  # noqa: BLE001 — no NVML binding: the nvidia-smi child
+            try:
+                cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)]
+                import shutil
+                if shutil.which("stdbuf"):
+                    cmd = ["stdbuf", "-oL"] + cmd
+                self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi -lms 50"
+            except OSError:
+                self.source = None
+        self._stopped = False
 
     def stop(self):
-        if self.samples is not None:
+        if self._stopped:
             return
-        self.samples = []
+        self._stopped = True
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
         if self.proc is None:
             return
         self.proc.terminate()
@@ -199,17 +236,24 @@ class ClockSampler:
             self.samples.append((t, sm, mx, [n for n, v in zip(self.NAMES, f[6:10]) if v.lower().startswith("active")]))
 
     def window(self, t0: float, t1: float):
-        self.stop()
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
-        inside = [s for s in self.samples if t0 <= s[0] <= t1]
-        if not inside and self.samples:   # a window shorter than the sampling period: the nearest sample
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML / nvidia-smi"]}
+        if self.proc is not None:
+            self.stop()
+        samples = list(self.samples)
+        inside = [s for s in samples if t0 <= s[0] <= t1]
+        nearest = False
+        if not inside and samples:   # a window shorter than the sampling period: the nearest sample
             mid = 0.5 * (t0 + t1)
-            inside = [min(self.samples, key=lambda s: abs(s[0] - mid))]
+            inside = [min(samples, key=lambda s: abs(s[0] - mid))]
+            nearest = True
         reasons = sorted({r for s in inside for r in s[3]})
-        return {"sm_mhz": statistics.median(s[1] for s in inside) if inside else None,
-                "sm_max_mhz": max((s[2] for s in inside), default=None), "samples": len(inside), "reasons": reasons,
-                "window_s": round(t1 - t0, 3)}
+        out = {"sm_mhz": statistics.median(s[1] for s in inside) if inside else None,
+               "sm_max_mhz": max((s[2] for s in inside), default=None), "samples": len(inside), "reasons": reasons,
+               "window_s": round(t1 - t0, 3), "source": self.source}
+        if nearest:
+            out["note"] = "window shorter than the sampling period: nearest sample"
+        return out
 
 
 def measured_peak():
