@@ -148,14 +148,26 @@ static void release_cache(agpu_device* dev) {  // caller holds g_mem_mu
   dev->cached_bytes = 0;
 }
 
-// cudaMalloc is a "potentially unsafe" call while this thread captures a stream: allowed in
-// relaxed mode only, so switch the thread's capture mode around it
-static cudaError_t malloc_during_capture(void** out, size_t bytes) {
+// cudaMalloc, cudaHostAlloc, cudaEventDestroy ... are "potentially unsafe" calls while this thread
+// captures a stream: one of them invalidates the capture (error 901 on the next launch) unless the
+// thread is in relaxed mode, so the thread's capture mode is switched around them.  They can come
+// at any moment — a garbage-collected host object dropping an event in the middle of a recording.
+struct RelaxedCaptureMode {
   cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
-  cudaThreadExchangeStreamCaptureMode(&mode);
-  const cudaError_t e = cudaMalloc(out, bytes);
-  cudaThreadExchangeStreamCaptureMode(&mode);
-  return e;
+  RelaxedCaptureMode() { cudaThreadExchangeStreamCaptureMode(&mode); }
+  ~RelaxedCaptureMode() { cudaThreadExchangeStreamCaptureMode(&mode); }
+};
+
+static cudaError_t malloc_during_capture(void** out, size_t bytes) {
+  RelaxedCaptureMode relaxed;
+  return cudaMalloc(out, bytes);
+}
+
+static bool any_handle_capturing() {
+  std::lock_guard<std::mutex> reg(g_registry_mu);
+  for (agpu_device* d : g_registry)
+    if (d->capturing) return true;
+  return false;
 }
 
 extern "C" int agpu_alloc(agpu_device* dev, size_t bytes, void** out) {
@@ -308,6 +320,11 @@ extern "C" int agpu_trim(agpu_device* dev) {
 // ---------------------------------------------------------------------------------------------
 // one submit per recorded pipeline: stream capture -> CUDA graph (compute_pipeline.rs:259-273)
 // ---------------------------------------------------------------------------------------------
+static std::mutex g_graveyard_mu;
+static std::vector<agpu_graph*> g_graveyard;  // graphs dropped while some handle was recording
+
+static int destroy_graph_now(agpu_graph* g);
+
 extern "C" int agpu_graph_begin(agpu_device* dev) {
   if (!dev) return AGPU_ENODEVICE;
   if (dev->capturing) return AGPU_EINVAL;
@@ -366,6 +383,14 @@ extern "C" int agpu_graph_end(agpu_device* dev, agpu_graph** out) {
     return (int)ie;
   }
   *out = g;
+  {
+    std::vector<agpu_graph*> todo;
+    {
+      std::lock_guard<std::mutex> lock(g_graveyard_mu);
+      if (!any_handle_capturing()) todo.swap(g_graveyard);
+    }
+    for (agpu_graph* x : todo) destroy_graph_now(x);
+  }
   return 0;
 }
 
@@ -382,6 +407,20 @@ extern "C" uint64_t agpu_graph_kernel_count(agpu_graph* g) { return g ? g->kerne
 
 extern "C" int agpu_graph_destroy(agpu_graph* g) {
   if (!g) return 0;
+  // A host object owning an older graph is often dropped in the middle of the NEXT recording
+  // (the variable is rebound after the new pipeline began capturing).  Destroying a graph there
+  // would invalidate that capture: park it until no handle is recording.
+  std::vector<agpu_graph*> todo;
+  {
+    std::lock_guard<std::mutex> lock(g_graveyard_mu);
+    g_graveyard.push_back(g);
+    if (!any_handle_capturing()) todo.swap(g_graveyard);
+  }
+  for (agpu_graph* x : todo) destroy_graph_now(x);
+  return 0;
+}
+
+static int destroy_graph_now(agpu_graph* g) {
   if (g->exec) cudaGraphExecDestroy(g->exec);
   if (g->graph) cudaGraphDestroy(g->graph);
   {
@@ -457,12 +496,14 @@ extern "C" int agpu_sync(agpu_device* dev) {
 
 extern "C" int agpu_host_alloc(size_t bytes, void** out) {
   if (!out) return AGPU_EINVAL;
+  RelaxedCaptureMode relaxed;
   AGPU_CUDA(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
   return 0;
 }
 
 extern "C" int agpu_host_free(void* ptr) {
   if (!ptr) return 0;
+  RelaxedCaptureMode relaxed;
   AGPU_CUDA(cudaFreeHost(ptr));
   return 0;
 }
@@ -470,6 +511,7 @@ extern "C" int agpu_host_free(void* ptr) {
 extern "C" int agpu_event_create(agpu_event** out) {
   if (!out) return AGPU_EINVAL;
   agpu_event* e = new agpu_event();
+  RelaxedCaptureMode relaxed;
   cudaError_t err = cudaEventCreate(&e->ev);
   if (err != cudaSuccess) { delete e; return (int)err; }
   *out = e;
@@ -478,7 +520,10 @@ extern "C" int agpu_event_create(agpu_event** out) {
 
 extern "C" int agpu_event_destroy(agpu_event* ev) {
   if (!ev) return 0;
-  cudaEventDestroy(ev->ev);
+  {
+    RelaxedCaptureMode relaxed;
+    cudaEventDestroy(ev->ev);
+  }
   delete ev;
   return 0;
 }

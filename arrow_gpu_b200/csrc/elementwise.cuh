@@ -28,15 +28,14 @@
 template <class Op, class = void> struct IsJointOp : std::false_type {};
 template <class Op> struct IsJointOp<Op, std::void_t<decltype(Op::JOINT)>> : std::bool_constant<Op::JOINT> {};
 
+// one tile (kBlock * UNROLL granules + its bitmap words) of an element-wise op
 template <class Op, int UNROLL, class Bm>
-__global__ void __launch_bounds__(kBlock) ew_kernel(const Op op, const size_t n, const Bm bm) {
-  pdl_wait();               // launched with programmatic stream serialization: see AGPU_LAUNCH_PDL
-  pdl_launch_dependents();  // the next kernel may start launching once every CTA of this grid is resident
+__device__ __forceinline__ void ew_tile(const Op& op, const size_t n, const Bm& bm, const size_t tile, const bool last_tile) {
   constexpr int G = Op::G;
   const size_t n_gran = n / G;
   const size_t tile_gran = (size_t)kBlock * UNROLL;
-  const size_t g0 = (size_t)blockIdx.x * tile_gran + threadIdx.x;
-  if (((size_t)blockIdx.x + 1) * tile_gran <= n_gran) {
+  const size_t g0 = tile * tile_gran + threadIdx.x;
+  if ((tile + 1) * tile_gran <= n_gran) {
     typename Op::In in[UNROLL];
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) in[j] = op.load(g0 + (size_t)j * kBlock);
@@ -52,14 +51,26 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Op op, const size_t n,
       const size_t g = g0 + (size_t)j * kBlock;
       if (g < n_gran) op.run(g, op.load(g));
     }
-    if (blockIdx.x == gridDim.x - 1) {
+    if (last_tile) {
       const size_t i = n_gran * G + threadIdx.x;  // n - n_gran*G < G <= 16 < kBlock
       if (i < n) op.tail(i);
     }
   }
   constexpr int tile_words = kBlock * UNROLL * G / 32;
-  bm.tile((size_t)blockIdx.x * tile_words, tile_words, (n + 31) / 32);
+  bm.tile(tile * tile_words, tile_words, (n + 31) / 32);
 }
+
+template <class Op, int UNROLL, class Bm>
+__global__ void __launch_bounds__(kBlock) ew_kernel(const Op op, const size_t n, const Bm bm) {
+  pdl_wait();               // launched with programmatic stream serialization: see AGPU_LAUNCH_PDL
+  pdl_launch_dependents();  // the next kernel may start launching once every CTA of this grid is resident
+  ew_tile<Op, UNROLL, Bm>(op, n, bm, blockIdx.x, blockIdx.x == gridDim.x - 1);
+}
+
+// (A persistent grid-stride form of this kernel — sm_count x resident CTAs walking the tiles — was
+// measured on B200 and is 12 % SLOWER on the config-2 step (11.21 vs 10.02 ms): without software
+// pipelining across tiles every CTA alternates load-wait-store, while one tile per CTA lets the
+// block scheduler keep all load phases overlapped.  profiles/r02_persistent_ab.md.)
 
 // Fallback for buffers that are not 16-byte aligned: one row per thread, same results.
 template <class Op, class Bm>

@@ -639,6 +639,109 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
 }
 
 // --------------------------------------------------------------------------------------------
+// validity of the compacted rows, as its own bitmap-only pass
+// --------------------------------------------------------------------------------------------
+// Compacting the validity bits inside the value scatter costs a byte store per kept row plus a
+// ballot pass and a third barrier (f32 + validity ran at 0.67 of the roofline against 1.0 without).
+// The bits do not need the values: one thread takes one 32-row word of (selection, validity),
+// extracts the validity bits of the selected rows with a parallel-suffix "compress" (Hacker's
+// Delight 7-4: 5 rounds of shift/xor, no table, no loop over rows), and ORs the result at the
+// word's output bit position — the tile offsets are the ones the count pass already produced.
+// 0.25 B/row of traffic; the kernel is ALU-bound and a fraction of the value pass.
+__device__ __forceinline__ uint32_t compress_bits(uint32_t x, uint32_t m) {
+  x &= m;
+  uint32_t mk = ~m << 1;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    uint32_t mp = mk ^ (mk << 1);
+    mp ^= mp << 2;
+    mp ^= mp << 4;
+    mp ^= mp << 8;
+    mp ^= mp << 16;
+    const uint32_t mv = mp & m;
+    m = (m ^ mv) | (mv >> (1 << i));
+    const uint32_t t = x & mv;
+    x = (x ^ t) | (t >> (1 << i));
+    mk &= ~mp;
+  }
+  return x;
+}
+
+constexpr int kBitsTileWords = 256;                                   // one word per thread
+constexpr int kBitsTilesPerCta = kBitsTileWords / kFilterTileWords;   // = 2 count-tiles
+
+__global__ void __launch_bounds__(kBitsTileWords) filter_bits_kernel(const uint32_t* __restrict__ vsrc,
+                                                                     const uint32_t* __restrict__ mask,
+                                                                     const uint32_t* __restrict__ vmask, const size_t n,
+                                                                     const uint32_t* __restrict__ counts,
+                                                                     const uint64_t* __restrict__ group_offsets,
+                                                                     uint32_t* vout, const uint64_t cap) {
+  __shared__ uint32_t stage[kBitsTileWords + 2];
+  __shared__ uint32_t warp_tot[kBitsTileWords / 32];
+  __shared__ uint64_t off_s;
+  const size_t nwords = (n + 31) / 32;
+  const size_t tiles = (n + kFilterTileRows - 1) / kFilterTileRows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t w = (size_t)blockIdx.x * kBitsTileWords + threadIdx.x;
+  const uint32_t s = sel_word(mask, vmask, w, nwords, n);
+  const uint32_t v = w < nwords ? vsrc[w] : 0u;
+  stage[threadIdx.x] = 0u;
+  if (threadIdx.x < 2) stage[kBitsTileWords + threadIdx.x] = 0u;
+  if (warp == 1) {  // output offset of this CTA's first row: group offset + counts of the earlier tiles of the group
+    const size_t t0 = (size_t)blockIdx.x * kBitsTilesPerCta;
+    const size_t gstart = t0 / kFilterGroupTiles * kFilterGroupTiles;
+    uint32_t before = 0;
+    if (gstart + lane < t0 && gstart + lane < tiles) before += counts[gstart + lane];
+    if (gstart + 32 + lane < t0 && gstart + 32 + lane < tiles) before += counts[gstart + 32 + lane];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
+    if (lane == 0) off_s = group_offsets[t0 / kFilterGroupTiles] + before;
+  }
+  const uint32_t c = __popc(s);
+  const uint32_t cv = compress_bits(v, s);
+  uint32_t incl = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+    if (lane >= off) incl += x;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < kBitsTileWords / 32; ++k) {
+    const uint32_t t = warp_tot[k];
+    if (k < warp) base += t;
+    total += t;
+  }
+  if (total == 0) return;  // uniform
+  const uint64_t off = off_s;
+  if (off >= cap) return;  // uniform
+  const uint32_t lead = (uint32_t)(off & 31);
+  const uint32_t pb = lead + base + (incl - c);  // bit position inside the staged words
+  if (c) {
+    atomicOr(&stage[pb >> 5], cv << (pb & 31));
+    if ((pb & 31) + c > 32) atomicOr(&stage[(pb >> 5) + 1], cv >> (32 - (pb & 31)));
+  }
+  __syncthreads();
+  // staged word j is output word (off >> 5) + j; the first and the last one are shared with the
+  // neighbouring CTAs (vout was zeroed by the host side), the ones in between are whole
+  const uint64_t room = cap - off;                                   // bits this CTA may still write
+  const uint32_t bits = (uint32_t)(total < room ? total : room);
+  const uint32_t nw = (lead + bits + 31) / 32;
+  const uint64_t gw0 = off >> 5;
+  for (uint32_t j = threadIdx.x; j < nw; j += kBitsTileWords) {
+    uint32_t val = stage[j];
+    if (j == nw - 1 && ((lead + bits) & 31)) val &= (1u << ((lead + bits) & 31)) - 1u;   // clip at the capacity
+    if ((j == 0 && lead) || j == nw - 1) {
+      if (val) atomicOr(vout + gw0 + j, val);
+    } else {
+      vout[gw0 + j] = val;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // TMA-staged variant of the scatter pass (opt-in with AGPU_FILTER_TMA=1; measured slower, see
 // run_filter).
 // Persistent CTAs walk tiles round-robin.  The 16 KiB of rows of the NEXT tile are fetched by
@@ -886,15 +989,21 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
     return launch_filter_tma<U, false>(dev, (const U*)src, vsrc, mask, vmask, n, sc, (U*)out, vout, cap);
   }
   // 512- and 1024-thread CTAs measured 10-50 % slower (profiles/r01_filter_variants.md)
+  static const bool fused_validity = getenv("AGPU_FILTER_FUSED_VALIDITY") != nullptr;  // A/B: the round-1 single kernel
   if (vsrc && vout) {
-    // only the words the compacted rows can reach are cleared (the kernel ORs bit groups into them)
+    // only the words the compacted rows can reach are cleared (the kernels OR bit groups into them)
     AGPU_CUDA(cudaMemsetAsync(vout, 0, ((cap + 31) / 32) * 4, dev->stream));
-    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
-                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
-  } else {
-    AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
-                vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
+    if (fused_validity) {
+      AGPU_LAUNCH(dev, (filter_scatter_kernel<U, true, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
+                  vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
+      return agpu_finish_launch();
+    }
+    const size_t bit_ctas = ceil_div(ceil_div(n, (size_t)32), (size_t)kBitsTileWords);
+    AGPU_LAUNCH(dev, filter_bits_kernel, (unsigned)bit_ctas, kBitsTileWords, 0, vsrc, mask, vmask, n, sc.counts,
+                sc.group_offsets, vout, (uint64_t)cap);
   }
+  AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
+              vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
   return agpu_finish_launch();
 }
 

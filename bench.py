@@ -414,7 +414,9 @@ def run_ours(args, rank, world, local_rank, sampler, numa):
         resident_step(step_events[s])
     dev.sync()
     t_window1 = time.time()
-    per_op_ms = [statistics.mean(ev.ms(step_events[s][k], step_events[s][k + 1]) for s in range(args.steps))
+    # median over the K passes: one host hiccup (GC, a page fault) while the queue is shallow lands
+    # in whichever op was waiting for its launch and would otherwise dominate its mean
+    per_op_ms = [statistics.median(ev.ms(step_events[s][k], step_events[s][k + 1]) for s in range(args.steps))
                  for k in range(len(ops))]
     peak, peak_src = measured_peak()
     per_op = {}
@@ -670,6 +672,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-per-config", action="store_true")
+    ap.add_argument("--per-config-only", default=None, help="debugging: skip config 2 and run only these per_config blocks (cfg1,cfg3,...)")
     ap.add_argument("--per-config-scale", type=float, default=1.0,
                     help="shrink the per_config row counts (smoke runs on small GPUs); 1.0 = BASELINE.json sizes")
     args = ap.parse_args()
@@ -716,6 +719,17 @@ def main():
                 emit(res)
             return 0
         from arrow_gpu_b200 import sharded
+        if args.per_config_only:
+            import arrow_gpu_b200 as ag
+            import bench_workloads
+            handles = tuple(ag.GpuDevice(local_rank) for _ in range(3))
+            per_config = bench_workloads.per_config(args, rank, world, local_rank, helpers, handles)
+            for block in per_config.values():
+                if isinstance(block, dict) and "_window" in block:
+                    block["clocks"] = sampler.window(*block.pop("_window"))
+            if rank == 0:
+                emit({"per_config": per_config})
+            return 0
         res = run_ours(args, rank, world, local_rank, sampler, numa)
         res["host_numa"] = numa.info
         cpu = None

@@ -618,9 +618,9 @@ def _cfg1_block(ctx, args, peak, handles, numa):
                             "ms_per_step": round(e2e_s * 1e3, 4)}
             for buf in (pa, pb, pva, pvb, land):
                 dev.pinned_free(buf)
-            del a, b, s, g
+            del a, b
         block["sizes"][f"{n} rows"] = entry
-        del progs, pairs, ops, ex
+        del progs, pairs, ops, ex, p, s, g
         import gc
         gc.collect()
     block["_window"] = (window0, time.time())
@@ -873,14 +873,22 @@ def per_config(args, rank, world, local_rank, helpers, handles):
     if world == 1:
         todo = [("cfg1", lambda c: _cfg1_block(c, args, peak, handles, numa)),
                 ("cfg3", lambda c: _cfg3_block(c, args, peak, handles, numa, scale))] + todo
+    only = getattr(args, "per_config_only", None)
+    if only:
+        todo = [t for t in todo if t[0] in only.split(",")]
     for name, fn in todo:
         ctx = Ctx(rank, world, local_rank, dev=handles[0])
         t0 = time.time()
         try:
             block = fn(ctx)
         except Exception as exc:  # noqa: BLE001 — one config must not take the whole bench line down
+            import sys
             import traceback
+            traceback.print_exc(file=sys.stderr)
             block = {"error": f"{type(exc).__name__}: {exc}"[:400], "trace": traceback.format_exc()[-1200:]}
+            h = C.c_void_p()   # an exception inside a captured pipeline leaves the stream capturing: close it
+            if ctx.lib.agpu_graph_end(ctx.dev.handle, C.byref(h)) == 0 and h:
+                ctx.lib.agpu_graph_destroy(h)
         block["seconds"] = round(time.time() - t0, 1)
         out[name] = block
         ctx.release()

@@ -268,3 +268,28 @@ def test_handles_of_several_ordinals_and_worker_threads(device):
     assert len(outs) == 2 * len(devices)
     for v in outs.values():
         assert np.array_equal(v, x * 6)
+
+
+def test_host_objects_dropped_in_the_middle_of_a_recording(device):
+    """A pipeline variable rebound inside a loop drops the PREVIOUS graph after the next recording
+    has begun; events and pinned buffers can go at any moment too (garbage collection).  None of
+    that may invalidate the capture in progress (CUDA error 901 on the next launch)."""
+    n = 50_000
+    x_h = np.arange(n, dtype=np.int32)
+    x = ag.Int32ArrayGPU.from_numpy(x_h, None, device)
+    outs = []
+    p = None
+    for k in range(4):
+        p = ag.ArrowComputePipeline(device, f"loop{k}", capture=True)   # rebinding drops graph k-1 here
+        ev = ag.GpuEvent()
+        pin = device.pinned_empty(1024, np.uint8)
+        y = x.add_op(x, p)
+        del ev                                                          # cudaEventDestroy while recording
+        device.pinned_free(pin)
+        z = y.bitwise_xor_op(x, p)
+        p.finish()
+        outs.append(z)
+    for z in outs:
+        assert np.array_equal(z.raw_values(), (x_h + x_h) ^ x_h)
+    p.replay()
+    assert np.array_equal(outs[-1].raw_values(), (x_h + x_h) ^ x_h)
