@@ -83,6 +83,9 @@ static int launch_bits(agpu_device* dev, const Op& op, uint32_t* out, size_t n, 
   if (aligned) {
     const size_t grid = ceil_div(n, (size_t)kBlock * UNROLL * Op::G);
     if (grid > 0x7FFFFFFFull) return AGPU_EINVAL;
+    if constexpr (UNROLL > 1 && !IsJointOp<Op>::value) {  // small columns: see launch_ew
+      if (grid < (size_t)4 * dev->sm_count) return launch_bits<Op, 1>(dev, op, out, n, bm, aligned);
+    }
     AGPU_LAUNCH_PDL(dev, (bits_kernel<Op, UNROLL>), (unsigned)grid, kBlock, 0, op, out, n, bm);
   } else {
     const size_t grid = ceil_div(n, (size_t)kBlock);

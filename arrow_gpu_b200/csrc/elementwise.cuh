@@ -90,6 +90,13 @@ static int launch_ew(agpu_device* dev, const Op& op, size_t n, const Bm& bm, boo
     const size_t tile_rows = (size_t)kBlock * UNROLL * Op::G;
     const size_t grid = ceil_div(n, tile_rows);
     if (grid > 0x7FFFFFFFull) return AGPU_EINVAL;
+    // Small columns (the reference's own sizes: <= 16 Mi rows per op, config 1 = 1 Mi): with UNROLL
+    // granules per thread a 1 Mi-row f32 op is only 256 CTAs = 1.7 per SM, so half the SMs do twice
+    // the work of the others and few loads are in flight.  One granule per thread gives 4x the CTAs,
+    // all resident at once: every load of the column is issued in the first microsecond.
+    if constexpr (UNROLL > 1 && !IsJointOp<Op>::value) {
+      if (grid < (size_t)4 * dev->sm_count) return launch_ew<Op, 1, Bm>(dev, op, n, bm, aligned);
+    }
     AGPU_LAUNCH_PDL(dev, (ew_kernel<Op, UNROLL, Bm>), (unsigned)grid, kBlock, 0, op, n, bm);
   } else {
     const size_t grid = ceil_div(n, (size_t)kBlock);

@@ -667,26 +667,63 @@ __device__ __forceinline__ uint32_t compress_bits(uint32_t x, uint32_t m) {
   return x;
 }
 
-constexpr int kBitsTileWords = 256;                                   // one word per thread
-constexpr int kBitsTilesPerCta = kBitsTileWords / kFilterTileWords;   // = 2 count-tiles
+// One thread owns kBitsWordsPerThread consecutive 32-row words (256 rows), so that it emits whole
+// output words by itself: compacted bits are appended to a 64-bit accumulator and every time 32 are
+// complete the low word goes straight to global memory with a plain store.  Only the first word (its
+// low bits belong to the previous thread) and the final partial word are OR-ed in atomically: two
+// reductions per 256 rows.  (A first version with one word per thread and shared-memory atomicOr
+// for every word was LSU-bound — ATOMS costs 2 cycles per lane on this part — and took 90 us for
+// 256 Mi rows; profiles/r02_filter_validity.md.)
+constexpr int kBitsWordsPerThread = 8;
+constexpr int kBitsBlock = 256;
+constexpr int kBitsCtaWords = kBitsBlock * kBitsWordsPerThread;          // 2048 words = 65536 rows
+constexpr int kBitsTilesPerCta = kBitsCtaWords / kFilterTileWords;        // = 16 count-tiles (divides the group size)
+static_assert(kFilterGroupTiles % kBitsTilesPerCta == 0, "a CTA's tiles must lie in one group");
 
-__global__ void __launch_bounds__(kBitsTileWords) filter_bits_kernel(const uint32_t* __restrict__ vsrc,
-                                                                     const uint32_t* __restrict__ mask,
-                                                                     const uint32_t* __restrict__ vmask, const size_t n,
-                                                                     const uint32_t* __restrict__ counts,
-                                                                     const uint64_t* __restrict__ group_offsets,
-                                                                     uint32_t* vout, const uint64_t cap) {
-  __shared__ uint32_t stage[kBitsTileWords + 2];
-  __shared__ uint32_t warp_tot[kBitsTileWords / 32];
+__device__ __forceinline__ void emit_bits(uint32_t* vout, uint64_t word_index, uint32_t word, bool atomic, uint64_t cap) {
+  const uint64_t bit0 = word_index * 32;
+  if (bit0 >= cap) return;                                            // past the capacity of the output
+  if (cap - bit0 < 32) word &= (1u << (uint32_t)(cap - bit0)) - 1u;   // the capacity ends inside this word
+  if (atomic) {
+    if (word) atomicOr(vout + word_index, word);
+  } else {
+    vout[word_index] = word;
+  }
+}
+
+__global__ void __launch_bounds__(kBitsBlock) filter_bits_kernel(const uint32_t* __restrict__ vsrc,
+                                                                 const uint32_t* __restrict__ mask,
+                                                                 const uint32_t* __restrict__ vmask, const size_t n,
+                                                                 const uint32_t* __restrict__ counts,
+                                                                 const uint64_t* __restrict__ group_offsets,
+                                                                 uint32_t* vout, const uint64_t cap, const int vec) {
+  __shared__ uint32_t warp_tot[kBitsBlock / 32];
   __shared__ uint64_t off_s;
   const size_t nwords = (n + 31) / 32;
   const size_t tiles = (n + kFilterTileRows - 1) / kFilterTileRows;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t w = (size_t)blockIdx.x * kBitsTileWords + threadIdx.x;
-  const uint32_t s = sel_word(mask, vmask, w, nwords, n);
-  const uint32_t v = w < nwords ? vsrc[w] : 0u;
-  stage[threadIdx.x] = 0u;
-  if (threadIdx.x < 2) stage[kBitsTileWords + threadIdx.x] = 0u;
+  const size_t w0 = ((size_t)blockIdx.x * kBitsBlock + threadIdx.x) * kBitsWordsPerThread;
+  uint32_t sel[kBitsWordsPerThread], val[kBitsWordsPerThread];
+  if (vec && w0 + kBitsWordsPerThread <= nwords && (w0 + kBitsWordsPerThread) * 32 <= n) {
+    // full words only: two 16-byte loads per bitmap
+#pragma unroll
+    for (int q = 0; q < kBitsWordsPerThread / 4; ++q) {
+      uint4 m = __ldg(reinterpret_cast<const uint4*>(mask + w0) + q);
+      if (vmask) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(vmask + w0) + q);
+        m.x &= x.x; m.y &= x.y; m.z &= x.z; m.w &= x.w;
+      }
+      const uint4 y = __ldg(reinterpret_cast<const uint4*>(vsrc + w0) + q);
+      sel[4 * q] = m.x; sel[4 * q + 1] = m.y; sel[4 * q + 2] = m.z; sel[4 * q + 3] = m.w;
+      val[4 * q] = y.x; val[4 * q + 1] = y.y; val[4 * q + 2] = y.z; val[4 * q + 3] = y.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kBitsWordsPerThread; ++k) {
+      sel[k] = sel_word(mask, vmask, w0 + k, nwords, n);
+      val[k] = w0 + k < nwords ? vsrc[w0 + k] : 0u;
+    }
+  }
   if (warp == 1) {  // output offset of this CTA's first row: group offset + counts of the earlier tiles of the group
     const size_t t0 = (size_t)blockIdx.x * kBitsTilesPerCta;
     const size_t gstart = t0 / kFilterGroupTiles * kFilterGroupTiles;
@@ -697,8 +734,9 @@ __global__ void __launch_bounds__(kBitsTileWords) filter_bits_kernel(const uint3
     for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
     if (lane == 0) off_s = group_offsets[t0 / kFilterGroupTiles] + before;
   }
-  const uint32_t c = __popc(s);
-  const uint32_t cv = compress_bits(v, s);
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < kBitsWordsPerThread; ++k) c += __popc(sel[k]);
   uint32_t incl = c;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -707,38 +745,32 @@ __global__ void __launch_bounds__(kBitsTileWords) filter_bits_kernel(const uint3
   }
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  uint32_t base = 0, total = 0;
+  uint32_t base = 0;
 #pragma unroll
-  for (int k = 0; k < kBitsTileWords / 32; ++k) {
-    const uint32_t t = warp_tot[k];
-    if (k < warp) base += t;
-    total += t;
-  }
-  if (total == 0) return;  // uniform
-  const uint64_t off = off_s;
-  if (off >= cap) return;  // uniform
-  const uint32_t lead = (uint32_t)(off & 31);
-  const uint32_t pb = lead + base + (incl - c);  // bit position inside the staged words
-  if (c) {
-    atomicOr(&stage[pb >> 5], cv << (pb & 31));
-    if ((pb & 31) + c > 32) atomicOr(&stage[(pb >> 5) + 1], cv >> (32 - (pb & 31)));
-  }
-  __syncthreads();
-  // staged word j is output word (off >> 5) + j; the first and the last one are shared with the
-  // neighbouring CTAs (vout was zeroed by the host side), the ones in between are whole
-  const uint64_t room = cap - off;                                   // bits this CTA may still write
-  const uint32_t bits = (uint32_t)(total < room ? total : room);
-  const uint32_t nw = (lead + bits + 31) / 32;
-  const uint64_t gw0 = off >> 5;
-  for (uint32_t j = threadIdx.x; j < nw; j += kBitsTileWords) {
-    uint32_t val = stage[j];
-    if (j == nw - 1 && ((lead + bits) & 31)) val &= (1u << ((lead + bits) & 31)) - 1u;   // clip at the capacity
-    if ((j == 0 && lead) || j == nw - 1) {
-      if (val) atomicOr(vout + gw0 + j, val);
-    } else {
-      vout[gw0 + j] = val;
+  for (int k = 0; k < kBitsBlock / 32; ++k)
+    if (k < warp) base += warp_tot[k];
+  if (c == 0) return;
+  const uint64_t pos = off_s + base + (incl - c);   // output bit position of this thread's first kept row
+  if (pos >= cap) return;
+  uint64_t wp = pos >> 5;
+  const uint32_t lead = (uint32_t)(pos & 31);
+  uint64_t acc = 0;
+  uint32_t nacc = lead;
+  bool first = true;
+#pragma unroll
+  for (int k = 0; k < kBitsWordsPerThread; ++k) {
+    const uint32_t cv = compress_bits(val[k], sel[k]);
+    acc |= (uint64_t)cv << nacc;
+    nacc += __popc(sel[k]);
+    if (nacc >= 32) {
+      emit_bits(vout, wp, (uint32_t)acc, first && lead != 0, cap);   // the first word is shared with the previous thread
+      ++wp;
+      acc >>= 32;
+      nacc -= 32;
+      first = false;
     }
   }
+  if (nacc > (first ? lead : 0u)) emit_bits(vout, wp, (uint32_t)acc, true, cap);  // partial: the next thread fills the rest
 }
 
 // --------------------------------------------------------------------------------------------
@@ -998,9 +1030,10 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
                   vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
       return agpu_finish_launch();
     }
-    const size_t bit_ctas = ceil_div(ceil_div(n, (size_t)32), (size_t)kBitsTileWords);
-    AGPU_LAUNCH(dev, filter_bits_kernel, (unsigned)bit_ctas, kBitsTileWords, 0, vsrc, mask, vmask, n, sc.counts,
-                sc.group_offsets, vout, (uint64_t)cap);
+    const size_t bit_ctas = ceil_div(ceil_div(n, (size_t)32), (size_t)kBitsCtaWords);
+    const int vec = aligned16(vsrc) && aligned16(mask) && (!vmask || aligned16(vmask));
+    AGPU_LAUNCH(dev, filter_bits_kernel, (unsigned)bit_ctas, kBitsBlock, 0, vsrc, mask, vmask, n, sc.counts,
+                sc.group_offsets, vout, (uint64_t)cap, vec);
   }
   AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
               vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
