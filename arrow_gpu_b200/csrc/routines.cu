@@ -691,6 +691,40 @@ __device__ __forceinline__ void emit_bits(uint32_t* vout, uint64_t word_index, u
   }
 }
 
+template <bool CLIP>
+__device__ __forceinline__ void compact_words(uint32_t* vout, uint64_t wp, const uint32_t lead,
+                                              const uint32_t (&sel)[kBitsWordsPerThread], const uint32_t (&val)[kBitsWordsPerThread],
+                                              const uint64_t cap) {
+  uint32_t* out = vout + wp;
+  uint64_t acc = 0;
+  uint32_t nacc = lead;
+  bool first = true;
+#pragma unroll
+  for (int k = 0; k < kBitsWordsPerThread; ++k) {
+    const uint32_t cv = compress_bits(val[k], sel[k]);
+    acc |= (uint64_t)cv << nacc;
+    nacc += __popc(sel[k]);
+    if (nacc >= 32) {
+      const bool shared_word = first && lead != 0;   // its low bits belong to the previous thread
+      if constexpr (CLIP) {
+        emit_bits(vout, wp, (uint32_t)acc, shared_word, cap);
+        ++wp;
+      } else {
+        if (shared_word) atomicOr(out, (uint32_t)acc);
+        else *out = (uint32_t)acc;
+        ++out;
+      }
+      acc >>= 32;
+      nacc -= 32;
+      first = false;
+    }
+  }
+  if (nacc > (first ? lead : 0u)) {  // partial last word: the next thread fills the rest
+    if constexpr (CLIP) emit_bits(vout, wp, (uint32_t)acc, true, cap);
+    else atomicOr(out, (uint32_t)acc);
+  }
+}
+
 __global__ void __launch_bounds__(kBitsBlock) filter_bits_kernel(const uint32_t* __restrict__ vsrc,
                                                                  const uint32_t* __restrict__ mask,
                                                                  const uint32_t* __restrict__ vmask, const size_t n,
@@ -752,25 +786,9 @@ __global__ void __launch_bounds__(kBitsBlock) filter_bits_kernel(const uint32_t*
   if (c == 0) return;
   const uint64_t pos = off_s + base + (incl - c);   // output bit position of this thread's first kept row
   if (pos >= cap) return;
-  uint64_t wp = pos >> 5;
   const uint32_t lead = (uint32_t)(pos & 31);
-  uint64_t acc = 0;
-  uint32_t nacc = lead;
-  bool first = true;
-#pragma unroll
-  for (int k = 0; k < kBitsWordsPerThread; ++k) {
-    const uint32_t cv = compress_bits(val[k], sel[k]);
-    acc |= (uint64_t)cv << nacc;
-    nacc += __popc(sel[k]);
-    if (nacc >= 32) {
-      emit_bits(vout, wp, (uint32_t)acc, first && lead != 0, cap);   // the first word is shared with the previous thread
-      ++wp;
-      acc >>= 32;
-      nacc -= 32;
-      first = false;
-    }
-  }
-  if (nacc > (first ? lead : 0u)) emit_bits(vout, wp, (uint32_t)acc, true, cap);  // partial: the next thread fills the rest
+  if (pos + c <= cap) compact_words<false>(vout, pos >> 5, lead, sel, val, cap);  // the usual case: no capacity checks per word
+  else compact_words<true>(vout, pos >> 5, lead, sel, val, cap);
 }
 
 // --------------------------------------------------------------------------------------------
