@@ -171,6 +171,14 @@ class GpuDevice:
     def retrive_data(self, buffer: "ArrowGpuBuffer", nbytes: Optional[int] = None) -> np.ndarray:
         """gpu_device.rs:232-265 — the only host synchronisation point"""
         n = buffer.size if nbytes is None else nbytes
+        if 0 < n <= 256:
+            # counts, flags, one-element results: through a pinned staging word (a pageable
+            # destination makes the driver stage the copy, ~15 us on top of the synchronisation)
+            stage = getattr(self, "_small_pinned", None)
+            if stage is None:
+                stage = self._small_pinned = self.pinned_empty(256, np.uint8)
+            check(lib().agpu_d2h(self.handle, stage.ctypes.data, buffer.ptr, n), "agpu_d2h")
+            return stage[:n].copy()
         out = np.empty(n, dtype=np.uint8)
         check(lib().agpu_d2h(self.handle, out.ctypes.data, buffer.ptr, n), "agpu_d2h")
         return out

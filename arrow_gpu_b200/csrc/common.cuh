@@ -42,6 +42,7 @@ struct agpu_device {
   unsigned long long capture_launches0 = 0;
   std::vector<void*> capture_freed;
   int pdl = 1;                               // programmatic dependent launch for the streaming kernels
+  unsigned int* ticket = nullptr;            // device word, zero between launches: "last CTA done" of filter_count
 };
 
 struct agpu_event {

@@ -65,6 +65,9 @@ extern "C" int agpu_device_create(int ordinal, agpu_device** out) {
   unsigned long long threshold = ~0ull;
   cudaMemPoolSetAttribute(d->pool, cudaMemPoolAttrReleaseThreshold, &threshold);
   cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, ordinal);
+  // one zeroed device word per handle: the "last CTA done" ticket of filter_count (routines.cu)
+  if (cudaMalloc((void**)&d->ticket, 256) == cudaSuccess) cudaMemset(d->ticket, 0, 256);
+  else d->ticket = nullptr;
   // experiment knobs: L2 -> DRAM fetch granularity hint in bytes (32/64/128), and PDL off
   if (const char* g = getenv("AGPU_L2_FETCH_GRANULARITY")) {
     const size_t v = (size_t)atoi(g);
@@ -98,6 +101,7 @@ extern "C" int agpu_device_destroy(agpu_device* dev) {
     }
   }
   cudaStreamSynchronize(dev->stream);
+  if (dev->ticket) cudaFree(dev->ticket);
   cudaEventDestroy(dev->order_event);
   cudaStreamDestroy(dev->stream);
   delete dev;

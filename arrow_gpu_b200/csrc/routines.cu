@@ -332,11 +332,61 @@ __device__ __forceinline__ uint32_t sel_word(const uint32_t* mask, const uint32_
   return s;
 }
 
+// exclusive scan of the group totals (in place) by ONE CTA of BLOCK threads, 8 values per thread per round
+template <int BLOCK>
+__device__ __forceinline__ void scan_group_totals(uint64_t* groups, const size_t n_groups, unsigned long long* total) {
+  __shared__ uint64_t scan_warp_tot[BLOCK / 32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t base = 0; base < n_groups; base += (size_t)BLOCK * 8) {
+    const size_t g0 = base + (size_t)threadIdx.x * 8;
+    uint64_t c[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      c[k] = g0 + k < n_groups ? __ldcg(groups + g0 + k) : 0ull;   // written by other CTAs of this launch: bypass L1
+      sum += c[k];
+    }
+    uint64_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint64_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) scan_warp_tot[warp] = incl;
+    __syncthreads();
+    uint64_t before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < BLOCK / 32; ++k) {
+      const uint64_t t = scan_warp_tot[k];
+      if (k < warp) before += t;
+      all += t;
+    }
+    uint64_t excl = carry_s + (incl - sum) + before;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (g0 + k < n_groups) groups[g0 + k] = excl;
+      excl += c[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+
+// The scan of the group totals rides in the count kernel: every CTA takes a ticket after publishing
+// its total, and the CTA that draws the last one scans all of them (threadfence reduction pattern).
+// One launch and one ~5 us single-CTA kernel less per filter; `ticket` lives in the device handle,
+// is zero between launches (the last CTA resets it) and launches of one handle are stream-ordered.
 __global__ void __launch_bounds__(kBlock) filter_count_kernel(const uint32_t* __restrict__ mask,
                                                               const uint32_t* __restrict__ vmask, const size_t n,
                                                               uint32_t* __restrict__ counts,
-                                                              uint64_t* __restrict__ group_totals, const int vec) {
+                                                              uint64_t* group_totals, const int vec,
+                                                              unsigned int* ticket, unsigned long long* total) {
   __shared__ uint32_t warp_tot[kBlock / 32];
+  __shared__ bool is_last;
   const size_t nwords = (n + 31) / 32;
   const size_t tiles = (n + kFilterTileRows - 1) / kFilterTileRows;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -379,55 +429,14 @@ __global__ void __launch_bounds__(kBlock) filter_count_kernel(const uint32_t* __
     uint64_t tot = 0;
     for (int w = 0; w < kBlock / 32; ++w) tot += warp_tot[w];
     group_totals[blockIdx.x] = tot;
+    __threadfence();                                        // the total is visible before the ticket
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
-}
-
-// single-CTA exclusive scan of the group totals (in place), 8 per thread per round
-__global__ void __launch_bounds__(1024) filter_scan_kernel(uint64_t* __restrict__ groups, const size_t n_groups,
-                                                           unsigned long long* __restrict__ total) {
-  __shared__ uint64_t warp_tot[32];
-  __shared__ uint64_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (size_t base = 0; base < n_groups; base += 1024 * 8) {
-    const size_t g0 = base + (size_t)threadIdx.x * 8;
-    uint64_t c[8], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      c[k] = g0 + k < n_groups ? groups[g0 + k] : 0ull;
-      sum += c[k];
-    }
-    uint64_t incl = sum;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const uint64_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-      if (lane >= off) incl += v;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      uint64_t w = warp_tot[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const uint64_t v = __shfl_up_sync(0xFFFFFFFFu, w, off);
-        if (lane >= off) w += v;
-      }
-      warp_tot[lane] = w;  // inclusive over warps
-    }
-    __syncthreads();
-    const uint64_t carry = carry_s;
-    uint64_t excl = carry + (incl - sum) + (warp ? warp_tot[warp - 1] : 0);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (g0 + k < n_groups) groups[g0 + k] = excl;
-      excl += c[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + warp_tot[31];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry_s;
+  if (!is_last) return;
+  __threadfence();                                          // every other CTA's total is visible now
+  scan_group_totals<kBlock>(group_totals, gridDim.x, total);
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // store `val` at shared-memory byte address `sa` and advance `sa` by one element iff bit != 0
@@ -1140,8 +1149,9 @@ extern "C" int agpu_filter_count(agpu_device* dev, const uint32_t* mask, const u
   const size_t groups = filter_groups(n);
   if (groups > 0x7FFFFFFFull) return AGPU_EINVAL;
   const int vec = aligned16(mask) && (!vmask || aligned16(vmask));
-  AGPU_LAUNCH(dev, filter_count_kernel, (unsigned)groups, kBlock, 0, mask, vmask, n, sc.counts, sc.group_offsets, vec);
-  AGPU_LAUNCH(dev, filter_scan_kernel, 1, 1024, 0, sc.group_offsets, groups, (unsigned long long*)total_dev);
+  if (!dev->ticket) return AGPU_ENODEVICE;
+  AGPU_LAUNCH(dev, filter_count_kernel, (unsigned)groups, kBlock, 0, mask, vmask, n, sc.counts, sc.group_offsets, vec, dev->ticket,
+              (unsigned long long*)total_dev);
   return agpu_finish_launch();
 }
 
