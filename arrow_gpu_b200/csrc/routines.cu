@@ -665,17 +665,18 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
 //     tail bytes fetched with one shuffle; lane 0 / lane 31 of a warp write their edge bytes singly;
 //   * a warp in which some thread keeps fewer than one word's worth of rows (low selectivity) takes
 //     the per-row path, which costs little there because few rows are stored at all.
+// One table entry compacts a PIECE = two packed words (8 x 1-byte rows, index = their 8 selection
+// bits; 4 x 2-byte rows, index = 4 bits): {prmt selector for the low word | selector for the high word
+// << 16, kept bytes, byte mask low, byte mask high} — one LDS.128 per piece.
 template <typename U>
-__device__ __forceinline__ void compact_word(uint32_t w, uint32_t bits, const uint32_t* lut, uint32_t& cw, uint32_t& cbytes) {
-  if constexpr (sizeof(U) == 1) {  // bits: 4 selection bits
-    const uint32_t e = lut[bits];
-    cw = __byte_perm(w, 0u, e);    // selector in the low 16 bits of e
-    cbytes = e >> 16;
-  } else {                         // bits: 2 selection bits
-    const uint32_t lo = (bits & 1u) ? (w & 0xFFFFu) : 0u;
-    cw = (bits & 2u) ? (lo | ((w >> 16) << ((bits & 1u) * 16))) : lo;
-    cbytes = __popc(bits) * 2;
-  }
+__device__ __forceinline__ uint4 narrow_lut_entry(uint32_t idx) {
+  constexpr int ES = sizeof(U);
+  uint32_t sel = 0, n = 0;  // n = kept bytes so far; selector nibble j = pool byte that lands in result byte j
+  for (int r = 0; r < 8 / ES; ++r)
+    if (idx & (1u << r))
+      for (int b = 0; b < ES; ++b) sel |= (uint32_t)(r * ES + b) << (4 * n++);
+  const unsigned long long m = n >= 8 ? ~0ull : ((1ull << (8 * n)) - 1ull);
+  return make_uint4(sel, n, (uint32_t)m, (uint32_t)(m >> 32));
 }
 
 template <typename U, int BLOCK>
@@ -694,11 +695,13 @@ __global__ void __launch_bounds__(BLOCK, 1280 / BLOCK) filter_scatter_narrow_ker
   constexpr int WORDS = ROWS / 32;                    // selection words per CTA
   constexpr int WPL = WORDS / 32;                     // selection words per lane of warp 0
   constexpr int SPT = RPT / 32;                       // selection words per thread (2 or 1)
-  constexpr int BPW = 4 / ES;                         // rows per packed 32-bit word
+  constexpr int RPP = 8 / ES;                         // rows per piece (two packed words)
+  constexpr int LUT = 1 << RPP;                       // 256 or 16 entries
+  static_assert(LUT <= BLOCK, "one table entry per thread");
   __shared__ __align__(16) uint32_t stage_w[ROWS * ES / 4 + 8];
+  __shared__ __align__(16) uint4 lut[LUT];
   __shared__ uint32_t sel[WORDS];
   __shared__ uint32_t pre[WORDS];
-  __shared__ uint32_t lut[16];
   __shared__ uint64_t off_s;
   __shared__ uint32_t count_s;
   U* stage = reinterpret_cast<U*>(stage_w);
@@ -720,13 +723,7 @@ __global__ void __launch_bounds__(BLOCK, 1280 / BLOCK) filter_scatter_narrow_ker
       w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
     }
   }
-  if (ES == 1 && threadIdx.x < 16) {  // prmt selectors: byte j of the result = j-th selected byte, the rest = 0 (index 4)
-    uint32_t sel16 = 0, c = 0;
-    for (int b = 0; b < 4; ++b)
-      if (threadIdx.x & (1 << b)) sel16 |= (uint32_t)b << (4 * c++);
-    for (int j = c; j < 4; ++j) sel16 |= 4u << (4 * j);
-    lut[threadIdx.x] = sel16 | (c << 16);
-  }
+  if (threadIdx.x < LUT) lut[threadIdx.x] = narrow_lut_entry<U>(threadIdx.x);
   uint32_t before = 0;
   uint64_t goff = 0;
   if (warp == 1) {
@@ -736,7 +733,15 @@ __global__ void __launch_bounds__(BLOCK, 1280 / BLOCK) filter_scatter_narrow_ker
     if (gstart + 32 + lane < t0) before += counts[gstart + 32 + lane];
     if (lane == 0) goff = group_offsets[t0 / kFilterGroupTiles];
   }
-  for (int k = threadIdx.x; k < WORDS; k += BLOCK) sel[k] = sel_word(mask, vmask, w0 + k, nwords, n);
+  if (full) {  // no ragged word, no bounds: plain loads
+    for (int k = threadIdx.x; k < WORDS; k += BLOCK) {
+      uint32_t x = mask[w0 + k];
+      if (vmask) x &= vmask[w0 + k];
+      sel[k] = x;
+    }
+  } else {
+    for (int k = threadIdx.x; k < WORDS; k += BLOCK) sel[k] = sel_word(mask, vmask, w0 + k, nwords, n);
+  }
   if (warp == 1) {
 #pragma unroll
     for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
@@ -766,37 +771,42 @@ __global__ void __launch_bounds__(BLOCK, 1280 / BLOCK) filter_scatter_narrow_ker
   const uint32_t lead = vec_out ? (uint32_t)(off % G) : 0u;
 
   if (full) {
-    uint64_t sbits = sel[threadIdx.x * SPT];
-    if constexpr (SPT == 2) sbits |= (uint64_t)sel[threadIdx.x * SPT + 1] << 32;
-    const uint32_t T = (uint32_t)__popcll(sbits) * ES;                 // bytes this thread keeps
-    const uint32_t P = (lead + pre[threadIdx.x * SPT]) * ES;           // byte offset of its run in the stage
+    uint32_t sb[2];
+    sb[0] = sel[threadIdx.x * SPT];
+    sb[1] = SPT == 2 ? sel[threadIdx.x * SPT + (SPT - 1)] : 0u;
+    const uint32_t T = (uint32_t)(__popc(sb[0]) + __popc(sb[1])) * ES;  // bytes this thread keeps
+    const uint32_t P = (lead + pre[threadIdx.x * SPT]) * ES;            // byte offset of its run in the stage
     const uint32_t a = P & 3u;
     // word path needs every thread of the warp to complete at least one word (so that each has a
     // first word to merge its predecessor's tail into)
     if (__all_sync(0xFFFFFFFFu, T + a >= 4u)) {
-      uint64_t acc = 0;
-      uint32_t nacc = a;                       // bytes in the accumulator; the low `a` are the predecessor's
-      uint32_t wp = P & ~3u;                   // byte address of the next word to emit
+      uint32_t a0 = 0;                         // pending bytes (< 4 after every piece); the low `a` are the predecessor's
+      uint32_t nacc = a;
+      uint32_t wp = P >> 2;                    // stage word that a0 will complete
       uint32_t w_first = 0;
-      bool first = true;
+      bool first = true;                       // the first completed word is held back (it shares bytes with the predecessor)
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        uint32_t cw, cb;
-        compact_word<U>(w[k], (uint32_t)(sbits >> (k * BPW)) & ((1u << BPW) - 1u), lut, cw, cb);
-        acc |= (uint64_t)cw << (8 * nacc);
-        nacc += cb;
-        if (nacc >= 4u) {
-          if (first) w_first = (uint32_t)acc;
-          else stage_w[wp >> 2] = (uint32_t)acc;
-          first = false;
-          wp += 4;
-          acc >>= 32;
-          nacc -= 4;
-        }
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t idx = (sb[(k * RPP) / 32] >> ((k * RPP) % 32)) & (uint32_t)(LUT - 1);
+        const uint4 e = lut[idx];
+        const uint32_t p0 = __byte_perm(w[2 * k], w[2 * k + 1], e.x) & e.z;
+        const uint32_t p1 = __byte_perm(w[2 * k], w[2 * k + 1], e.x >> 16) & e.w;
+        const uint32_t sh = nacc * 8;
+        a0 |= p0 << sh;
+        const uint32_t a1 = __funnelshift_l(p0, p1, sh);   // bytes 4..7 of (piece << sh)
+        const uint32_t a2 = __funnelshift_l(p1, 0u, sh);   // bytes 8..11
+        nacc += e.y;                                       // <= 11
+        const bool e1 = nacc >= 4u, e2 = nacc >= 8u;
+        if (e1 && !first) stage_w[wp] = a0;
+        if (e1 && first) w_first = a0;
+        if (e2) stage_w[wp + 1] = a1;
+        first = first && !e1;
+        a0 = e2 ? a2 : (e1 ? a1 : a0);
+        wp += nacc >> 2;
+        nacc &= 3u;
       }
       // the first word: own bytes | the previous lane's tail (its last `a` bytes)
-      const uint32_t tail = (uint32_t)acc;     // nacc (< 4) bytes; bytes above are zero
-      const uint32_t prev_tail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+      const uint32_t prev_tail = __shfl_up_sync(0xFFFFFFFFu, a0, 1);
       if (lane != 0) {
         stage_w[P >> 2] = w_first | prev_tail;
       } else {                                 // the predecessor is in another warp: it writes its own tail bytes
@@ -807,7 +817,7 @@ __global__ void __launch_bounds__(BLOCK, 1280 / BLOCK) filter_scatter_narrow_ker
       if (lane == 31) {                        // nobody in this warp picks up the last lane's tail
 #pragma unroll
         for (uint32_t b = 0; b < 3; ++b)
-          if (b < nacc) stage_b[wp + b] = (uint8_t)(tail >> (8 * b));
+          if (b < nacc) stage_b[wp * 4 + b] = (uint8_t)(a0 >> (8 * b));
       }
     } else {
       // per-row path (same as the wide kernel): predicated stores, one row at a time
@@ -815,7 +825,7 @@ __global__ void __launch_bounds__(BLOCK, 1280 / BLOCK) filter_scatter_narrow_ker
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t ww[4] = {w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]};
-        stage_lanes<U, 0>(sa, ww, (uint32_t)(sbits >> (q * G)));
+        stage_lanes<U, 0>(sa, ww, sb[(q * G) / 32] >> ((q * G) % 32));
       }
     }
   } else {
