@@ -648,218 +648,6 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
 }
 
 // --------------------------------------------------------------------------------------------
-// scatter pass for 1- and 2-byte rows: word-level compaction
-// --------------------------------------------------------------------------------------------
-// The kernel above stages ONE ROW per predicated st.shared: for 1-byte rows that is 10 thread-
-// instructions and one shared-memory wavefront per row, and the kernel is issue / shared-memory
-// bound at 0.40-0.67 of the HBM roofline (profiles/r02_filter_validity.md).  Here one thread owns
-// 64 CONTIGUOUS bytes of rows (64 x 1 byte or 32 x 2 bytes; the warp still reads whole 32-byte
-// sectors, each sector by one lane in two adjacent 16-byte loads), so its kept rows form one
-// contiguous run of the output and it can emit whole 4-byte words:
-//   * each packed input word is compacted on its own — 1-byte rows: the 4 selection bits index a
-//     16-entry table of `prmt` selectors (unused positions pick a zero byte); 2-byte rows: two
-//     selects — and appended to a 64-bit accumulator; whenever 4 bytes are complete the low word
-//     goes to the staging buffer with one aligned st.shared.b32;
-//   * the run starts at an arbitrary byte offset: the thread's FIRST word (whose low bytes belong to
-//     the previous thread) is held back and written after the loop, OR-ed with the previous lane's
-//     tail bytes fetched with one shuffle; lane 0 / lane 31 of a warp write their edge bytes singly;
-//   * a warp in which some thread keeps fewer than one word's worth of rows (low selectivity) takes
-//     the per-row path, which costs little there because few rows are stored at all.
-// One table entry compacts a PIECE = two packed words (8 x 1-byte rows, index = their 8 selection
-// bits; 4 x 2-byte rows, index = 4 bits): {prmt selector for the low word | selector for the high word
-// << 16, kept bytes, byte mask low, byte mask high} — one LDS.128 per piece.
-template <typename U>
-__device__ __forceinline__ uint4 narrow_lut_entry(uint32_t idx) {
-  constexpr int ES = sizeof(U);
-  uint32_t sel = 0, n = 0;  // n = kept bytes so far; selector nibble j = pool byte that lands in result byte j
-  for (int r = 0; r < 8 / ES; ++r)
-    if (idx & (1u << r))
-      for (int b = 0; b < ES; ++b) sel |= (uint32_t)(r * ES + b) << (4 * n++);
-  const unsigned long long m = n >= 8 ? ~0ull : ((1ull << (8 * n)) - 1ull);
-  return make_uint4(sel, n, (uint32_t)m, (uint32_t)(m >> 32));
-}
-
-template <typename U, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1280 / BLOCK) filter_scatter_narrow_kernel(const U* __restrict__ src,
-                                                                const uint32_t* __restrict__ mask,
-                                                                const uint32_t* __restrict__ vmask, const size_t n,
-                                                                const uint32_t* __restrict__ counts,
-                                                                const uint64_t* __restrict__ group_offsets,
-                                                                U* __restrict__ out, const uint64_t cap) {
-  static_assert(sizeof(U) == 1 || sizeof(U) == 2, "narrow rows only");
-  constexpr int ES = sizeof(U);
-  constexpr int G = 16 / ES;                          // rows per 16-byte vector of the output
-  constexpr int RPT = 64 / ES;                        // rows per thread: 64 contiguous bytes
-  constexpr int ROWS = BLOCK * RPT;                   // rows per CTA (16 KiB of rows)
-  constexpr int M = ROWS / kFilterTileRows;           // count-tiles per CTA
-  constexpr int WORDS = ROWS / 32;                    // selection words per CTA
-  constexpr int WPL = WORDS / 32;                     // selection words per lane of warp 0
-  constexpr int SPT = RPT / 32;                       // selection words per thread (2 or 1)
-  constexpr int RPP = 8 / ES;                         // rows per piece (two packed words)
-  constexpr int LUT = 1 << RPP;                       // 256 or 16 entries
-  static_assert(LUT <= BLOCK, "one table entry per thread");
-  __shared__ __align__(16) uint32_t stage_w[ROWS * ES / 4 + 8];
-  __shared__ __align__(16) uint4 lut[LUT];
-  __shared__ uint32_t sel[WORDS];
-  __shared__ uint32_t pre[WORDS];
-  __shared__ uint64_t off_s;
-  __shared__ uint32_t count_s;
-  U* stage = reinterpret_cast<U*>(stage_w);
-  uint8_t* stage_b = reinterpret_cast<uint8_t*>(stage_w);
-
-  const size_t tile = blockIdx.x;
-  const size_t nwords = (n + 31) / 32;
-  const size_t w0 = tile * WORDS;
-  const size_t row0 = tile * ROWS;
-  const bool full = row0 + ROWS <= n;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  uint32_t w[16];  // this thread's 64 bytes of rows, as packed words
-  if (full) {
-    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src + row0) + (size_t)threadIdx.x * 64);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint4 x = __ldcs(p + q);
-      w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
-    }
-  }
-  if (threadIdx.x < LUT) lut[threadIdx.x] = narrow_lut_entry<U>(threadIdx.x);
-  uint32_t before = 0;
-  uint64_t goff = 0;
-  if (warp == 1) {
-    const size_t t0 = tile * M;
-    const size_t gstart = t0 / kFilterGroupTiles * kFilterGroupTiles;
-    if (gstart + lane < t0) before += counts[gstart + lane];
-    if (gstart + 32 + lane < t0) before += counts[gstart + 32 + lane];
-    if (lane == 0) goff = group_offsets[t0 / kFilterGroupTiles];
-  }
-  if (full) {  // no ragged word, no bounds: plain loads
-    for (int k = threadIdx.x; k < WORDS; k += BLOCK) {
-      uint32_t x = mask[w0 + k];
-      if (vmask) x &= vmask[w0 + k];
-      sel[k] = x;
-    }
-  } else {
-    for (int k = threadIdx.x; k < WORDS; k += BLOCK) sel[k] = sel_word(mask, vmask, w0 + k, nwords, n);
-  }
-  if (warp == 1) {
-#pragma unroll
-    for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
-    if (lane == 0) off_s = goff + before;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t c[WPL], t = 0;
-#pragma unroll
-    for (int k = 0; k < WPL; ++k) { c[k] = __popc(sel[lane * WPL + k]); t += c[k]; }
-    uint32_t incl = t;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-      if (lane >= off) incl += x;
-    }
-    uint32_t e = incl - t;
-#pragma unroll
-    for (int k = 0; k < WPL; ++k) { pre[lane * WPL + k] = e; e += c[k]; }
-    if (lane == 31) count_s = incl;
-  }
-  __syncthreads();
-  const uint64_t off = off_s;
-  const uint32_t count = off >= cap ? 0u : (uint32_t)min((uint64_t)count_s, cap - off);
-  if (count == 0) return;  // uniform for the CTA
-  const bool vec_out = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-  const uint32_t lead = vec_out ? (uint32_t)(off % G) : 0u;
-
-  if (full) {
-    uint32_t sb[2];
-    sb[0] = sel[threadIdx.x * SPT];
-    sb[1] = SPT == 2 ? sel[threadIdx.x * SPT + (SPT - 1)] : 0u;
-    const uint32_t T = (uint32_t)(__popc(sb[0]) + __popc(sb[1])) * ES;  // bytes this thread keeps
-    const uint32_t P = (lead + pre[threadIdx.x * SPT]) * ES;            // byte offset of its run in the stage
-    const uint32_t a = P & 3u;
-    // word path needs every thread of the warp to complete at least one word (so that each has a
-    // first word to merge its predecessor's tail into)
-    if (__all_sync(0xFFFFFFFFu, T + a >= 4u)) {
-      uint32_t a0 = 0;                         // pending bytes (< 4 after every piece); the low `a` are the predecessor's
-      uint32_t nacc = a;
-      uint32_t wp = P >> 2;                    // stage word that a0 will complete
-      uint32_t w_first = 0;
-      bool first = true;                       // the first completed word is held back (it shares bytes with the predecessor)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t idx = (sb[(k * RPP) / 32] >> ((k * RPP) % 32)) & (uint32_t)(LUT - 1);
-        const uint4 e = lut[idx];
-        const uint32_t p0 = __byte_perm(w[2 * k], w[2 * k + 1], e.x) & e.z;
-        const uint32_t p1 = __byte_perm(w[2 * k], w[2 * k + 1], e.x >> 16) & e.w;
-        const uint32_t sh = nacc * 8;
-        a0 |= p0 << sh;
-        const uint32_t a1 = __funnelshift_l(p0, p1, sh);   // bytes 4..7 of (piece << sh)
-        const uint32_t a2 = __funnelshift_l(p1, 0u, sh);   // bytes 8..11
-        nacc += e.y;                                       // <= 11
-        const bool e1 = nacc >= 4u, e2 = nacc >= 8u;
-        if (e1 && !first) stage_w[wp] = a0;
-        if (e1 && first) w_first = a0;
-        if (e2) stage_w[wp + 1] = a1;
-        first = first && !e1;
-        a0 = e2 ? a2 : (e1 ? a1 : a0);
-        wp += nacc >> 2;
-        nacc &= 3u;
-      }
-      // the first word: own bytes | the previous lane's tail (its last `a` bytes)
-      const uint32_t prev_tail = __shfl_up_sync(0xFFFFFFFFu, a0, 1);
-      if (lane != 0) {
-        stage_w[P >> 2] = w_first | prev_tail;
-      } else {                                 // the predecessor is in another warp: it writes its own tail bytes
-#pragma unroll
-        for (uint32_t b = 0; b < 4; ++b)
-          if (b >= a) stage_b[(P & ~3u) + b] = (uint8_t)(w_first >> (8 * b));
-      }
-      if (lane == 31) {                        // nobody in this warp picks up the last lane's tail
-#pragma unroll
-        for (uint32_t b = 0; b < 3; ++b)
-          if (b < nacc) stage_b[wp * 4 + b] = (uint8_t)(a0 >> (8 * b));
-      }
-    } else {
-      // per-row path (same as the wide kernel): predicated stores, one row at a time
-      uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage_b) + P;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t ww[4] = {w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]};
-        stage_lanes<U, 0>(sa, ww, sb[(q * G) / 32] >> ((q * G) % 32));
-      }
-    }
-  } else {
-    // ragged last tile: one row at a time straight from global memory
-    for (int r = threadIdx.x * RPT; r < (threadIdx.x + 1) * RPT; r += 32) {
-      const uint32_t sw = sel[r >> 5];
-      if (sw == 0) continue;
-      uint32_t pos = lead + pre[r >> 5];
-      for (int k = 0; k < 32; ++k)
-        if ((sw >> k) & 1u) stage[pos++] = src[row0 + r + k];
-    }
-  }
-  __syncthreads();
-
-  if (vec_out) {
-    U* gbase = out + (off - lead);
-    const uint32_t end = lead + count;
-    const uint32_t nvec = (end + G - 1) / G;
-    for (uint32_t q = threadIdx.x; q < nvec; q += BLOCK) {
-      const uint32_t e0 = q * G;
-      if (e0 >= lead && e0 + G <= end) {
-        Vec<U, G> t = *reinterpret_cast<const Vec<U, G>*>(stage + e0);
-        st_vec<U, G>(gbase, q, t);
-      } else {
-        for (uint32_t k = 0; k < (uint32_t)G; ++k)
-          if (e0 + k >= lead && e0 + k < end) gbase[e0 + k] = stage[e0 + k];
-      }
-    }
-  } else {
-    for (uint32_t i = threadIdx.x; i < count; i += BLOCK) out[off + i] = stage[i];
-  }
-}
-
-// --------------------------------------------------------------------------------------------
 // validity of the compacted rows, as its own bitmap-only pass
 // --------------------------------------------------------------------------------------------
 // Compacting the validity bits inside the value scatter costs a byte store per kept row plus a
@@ -1274,14 +1062,9 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
     AGPU_LAUNCH(dev, filter_bits_kernel, (unsigned)bit_ctas, kBitsBlock, 0, vsrc, mask, vmask, n, sc.counts,
                 sc.group_offsets, vout, (uint64_t)cap, vec);
   }
-  if constexpr (sizeof(U) < 4) {
-    static const bool per_row = getenv("AGPU_FILTER_NARROW_PER_ROW") != nullptr;  // A/B: the round-1 kernel
-    if (!per_row) {
-      AGPU_LAUNCH(dev, (filter_scatter_narrow_kernel<U, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, mask, vmask, n,
-                  sc.counts, sc.group_offsets, (U*)out, (uint64_t)cap);
-      return agpu_finish_launch();
-    }
-  }
+  // (1- and 2-byte rows: a word-level scatter — 64 contiguous bytes per thread, table-driven prmt
+  // compaction of two packed words at a time, whole-word stores — was built and measured SLOWER than
+  // this per-row kernel: commit 1c67e8c, profiles/r02_filter_validity.md.)
   AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK>), (unsigned)super_tiles, BLOCK, 0, (const U*)src, vsrc, mask,
               vmask, n, sc.counts, sc.group_offsets, (U*)out, vout, (uint64_t)cap);
   return agpu_finish_launch();
