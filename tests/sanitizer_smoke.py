@@ -66,6 +66,23 @@ def main():
         assert np.array_equal(got.raw_values(), ia.bitwise_not().div(ia).gt(ia).raw_values())
         u16 = rng.integers(0, 65536, n).astype(np.uint16)
         assert np.array_equal(ag.UInt16ArrayGPU.from_numpy(u16, None, dev).filter(m).raw_values(), u16[flags & vb])
+        # round 2: host-free filter (scatter launched before the count is read, output sized for the
+        # shard), a captured pipeline replayed twice, put with out-of-range indices
+        from arrow_gpu_b200 import sharded
+        out, off, tot = sharded.sharded_filter_async(ia, m).result()
+        assert off == 0 and tot == out.len and np.array_equal(out.raw_values(), i32[flags & vb])
+        assert np.array_equal(out.null_buffer.flags(), va[flags & vb])
+        p = ag.ArrowComputePipeline(dev, "smoke", capture=True)
+        s1 = ia.add_op(ia, p)
+        g1 = s1.gt_op(ia, p)
+        p.finish()
+        p.replay()
+        p.replay()
+        assert np.array_equal(g1.raw_values(), (i32 + i32).astype(np.int32) > i32)
+        wild = idx.copy()
+        wild[::3] += np.uint32(n)          # every third index out of range: reads zero / writes nothing
+        ag.Int32ArrayGPU.from_numpy(i32, None, dev).put(ag.UInt32ArrayGPU.from_numpy(wild, None, dev), dst,
+                                                        ag.UInt32ArrayGPU.from_numpy(wild, None, dev))
     dev.sync()
     print("sanitizer smoke ok,", dev.launch_count(), "launches")
 
