@@ -14,7 +14,6 @@ pub mod boolean_gpu;
 pub mod buffer;
 pub mod null_bit_buffer;
 pub mod primitive_array_gpu;
-pub mod types;
 
 pub use boolean_gpu::BooleanArrayGPU;
 pub use null_bit_buffer::*;
@@ -102,6 +101,29 @@ pub type Int32ArrayGPU = PrimitiveArrayGpu<i32>;
 pub type Int16ArrayGPU = PrimitiveArrayGpu<i16>;
 pub type Int8ArrayGPU = PrimitiveArrayGpu<i8>;
 pub type Date32ArrayGPU = PrimitiveArrayGpu<Date32Type>;
+
+/// Marker traits grouping element types by their storage (the reference's `array/types.rs`), used
+/// by the operator crates' `impl<S: Int32Type> ... for Int32ArrayGPU` blocks (arithmetic/src/i32.rs)
+pub mod types {
+    use super::Date32Type;
+
+    /// Arrow Array backed by i32
+    pub trait Int32Type {}
+    impl Int32Type for i32 {}
+    impl Int32Type for Date32Type {}
+
+    /// Arrow Array backed by f32
+    pub trait Float32Type {}
+    impl Float32Type for f32 {}
+
+    /// Arrow Array backed by u32
+    pub trait UInt32Type {}
+    impl UInt32Type for u32 {}
+
+    /// Arrow Array backed by u16
+    pub trait UInt16Type {}
+    impl UInt16Type for u16 {}
+}
 
 /// array/mod.rs:96-99
 pub trait ArrayUtils {
