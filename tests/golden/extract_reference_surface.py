@@ -100,7 +100,7 @@ def surface_of_text(text: str, surface: dict) -> None:
         end = matching(cut, m.end() - 1, "(", ")")
         key = "dyn_functions" if m.group(1).endswith("_dyn") else "functions"
         surface[key][m.group(1)] = arity(cut[m.end():end])
-    for m in re.finditer(r"^pub\s+(enum|struct)\s+(\w+)", cut, flags=re.M):
+    for m in re.finditer(r"^\s*pub\s+(enum|struct)\s+(\w+)", cut, flags=re.M):
         surface["types"].setdefault(m.group(2), m.group(1))
 
 
