@@ -11,16 +11,23 @@
 #include <cstdio>
 #include <memory>
 #include <random>
+#include <string>
 
 #include "arrow_gpu.hpp"
 
 using namespace arrow_gpu;
 
-int main() {
+int main(int argc, char** argv) {
+  const bool json = argc > 1 && std::string(argv[1]) == "--json";   // one JSON object for bench.py's per_config.cfg1
   auto device = std::make_shared<GpuDevice>(0);
+  if (json) std::printf("{\"what\": \"C++ host mirror (arrow_gpu.hpp), f32 add + gt with null bitmaps, cold inputs (rotating copies >= 512 MiB), "
+                        "wall clock over >= 512 submissions; frac = algorithmic GB/s / 6541.1\", \"sizes\": {");
+  bool first_size = true;
   std::mt19937 rng(1);
   std::uniform_real_distribution<float> dist(-1000.f, 1000.f);
-  for (size_t n : {size_t(1) << 16, size_t(1) << 18, size_t(1) << 20, size_t(1) << 22, size_t(1) << 24}) {
+  std::vector<size_t> sizes = {size_t(1) << 16, size_t(1) << 18, size_t(1) << 20, size_t(1) << 22, size_t(1) << 24};
+  if (json) sizes = {size_t(1) << 20, size_t(1) << 22, size_t(1) << 24};
+  for (size_t n : sizes) {
     std::vector<std::optional<float>> a(n), b(n);
     for (size_t i = 0; i < n; ++i) {
       if (rng() % 10) a[i] = dist(rng);
@@ -61,9 +68,17 @@ int main() {
     device->sync();
     const double us_g = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / (2.0 * pairs);
     const double gbs_g = (12.375 + 8.5) / 2.0 * double(n) / us_g / 1e3;
+    if (json) {
+      std::printf("%s\"%zu rows\": {\"eager_us_per_op\": %.3f, \"eager_GBps\": %.1f, \"eager_frac_measured_peak\": %.4f, "
+                  "\"captured_us_per_op\": %.3f, \"captured_GBps\": %.1f, \"captured_frac_measured_peak\": %.4f, \"input_copies\": %zu}",
+                  first_size ? "" : ", ", n, us, gbs, gbs / 6541.1, us_g, gbs_g, gbs_g / 6541.1, copies);
+      first_size = false;
+      continue;
+    }
     std::printf("rows=2^%d  copies=%zu  eager %.2f us per op  %.0f GB/s (%.3f of 6541) | captured %.2f us per op  %.0f GB/s (%.3f of 6541)  "
                 "[mean of add and gt, validity included; %llu kernels per submit]\n", (int)std::log2((double)n), copies, us, gbs,
                 gbs / 6541.1, us_g, gbs_g, gbs_g / 6541.1, (unsigned long long)progs[0]->kernels_per_submit());
   }
+  if (json) std::printf("}}\n");
   return 0;
 }

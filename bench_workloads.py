@@ -625,6 +625,20 @@ def _cfg1_block(ctx, args, peak, handles, numa):
         gc.collect()
     block["_window"] = (window0, time.time())
     block["per_op"] = block["sizes"][f"{1 << 20} rows"]["per_op_eager"]
+    # the same config through the compiled host mirror (what a Rust caller of the crates would see):
+    # arrow_gpu_b200/cpp/bench_small links only libagpu.so; its own process, its own device handle
+    import json
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "arrow_gpu_b200", "cpp", "bench_small")
+    if os.path.exists(exe):
+        dev.sync()
+        try:
+            res = subprocess.run([exe, "--json"], capture_output=True, text=True, timeout=120,
+                                 env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx.local_rank))))
+            block["cpp_mirror"] = json.loads(res.stdout.strip().splitlines()[-1]) if res.returncode == 0 else {"error": res.stderr[-300:]}
+        except Exception as exc:  # noqa: BLE001
+            block["cpp_mirror"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     return block
 
 
