@@ -4,10 +4,10 @@
 // library call (launch + proxy + protocol, ~20-80 us) dwarfs the data: here every rank owns a small
 // slot area in cudaMalloc'ed memory that all peers have mapped through CUDA IPC, and
 //   post : one warp, lane r stores {tag, value} as ONE 64-bit word into slot[my_rank] of peer r
-//          (st.release.sys straight over NVLink/NVSwitch — a single word carries tag and value,
-//          so no separate flag and no fence ordering between two stores is needed)
+//          (st.relaxed.sys straight over NVLink/NVSwitch — a single word carries tag and value,
+//          so no separate flag, no fence and no release/acquire pairing is needed)
 //   wait : one warp, lane r polls its own slot[r] until the tag of this exchange shows up
-//          (ld.acquire.sys), then the warp prefix-sums the values into global offsets.
+//          (ld.relaxed.sys), then the warp prefix-sums the values into global offsets.
 // Both are ordinary kernels on the handle's stream: a sharded filter enqueues
 // count -> post -> scatter -> wait with no host synchronisation in between.
 //
@@ -39,7 +39,8 @@ __global__ void exchange_post_kernel(const unsigned long long* __restrict__ valu
   if (v > kValueMask) v = kValueMask;  // cannot happen for row counts (2^40 rows); keeps the tag intact
   const unsigned long long word = (exchange_tag(seq) << kValueBits) | v;
   unsigned long long* dst = peers.slots[r] + (size_t)(seq % AGPU_EXCHANGE_RING) * world + rank;
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+  // relaxed is enough: the one word carries tag AND value, nothing else is published with it
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
 }
 
 __global__ void exchange_wait_kernel(const unsigned long long* __restrict__ my_slots, const int world, const uint32_t seq,
@@ -54,7 +55,7 @@ __global__ void exchange_wait_kernel(const unsigned long long* __restrict__ my_s
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
       unsigned long long word;
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
       if ((word >> kValueBits) == want) { v = word & kValueMask; break; }
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (now - t0 > timeout_ns) { ok = 0; break; }  // a peer died or skipped the exchange: report, never hang
