@@ -190,3 +190,55 @@ def test_constructors_upload_the_reference_layout(stub):
     assert b.len == 34 and a.len == 5
     f = ag.Float32ArrayGPU.from_slice([1.0, -0.0], dev)
     assert f.null_buffer is None                                         # no nulls -> no bitmap (null_bit_buffer.rs:99-111)
+
+
+def test_put_on_a_fusing_pipeline_launches_the_recorded_chains_first(stub):
+    """put_op mutates `dst` at once; a chain recorded earlier on the same pipeline that
+    reads `dst` must be launched BEFORE the put (the reference's encoder order), and ops recorded
+    after it come after."""
+    lib, dev = stub
+    i32 = lambda n=64: ag.Int32ArrayGPU.from_slice([1] * n, dev)   # noqa: E731
+    dst, c, src = i32(), i32(), i32()
+    idx = ag.UInt32ArrayGPU.from_slice(list(range(8)), dev)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    y = dst.add_op(c, p)                       # recorded, not launched
+    assert lib.launched() == []
+    src.put_op(idx, dst, idx, p)               # in place: flushes the recorded chain first
+    order = [n for n, _a in lib.calls if n in LAUNCHING or n == "agpu_put"]
+    assert order == ["agpu_fused_chain_int", "agpu_put"], order
+    z = dst.add_op(c, p)                       # recorded after the put
+    p.finish()
+    order = [n for n, _a in lib.calls if n in LAUNCHING or n == "agpu_put"]
+    assert order == ["agpu_fused_chain_int", "agpu_put", "agpu_fused_chain_int"], order
+    put_args = [a for n, a in lib.calls if n == "agpu_put"][0]
+    assert put_args[3] == src.len and put_args[6] == dst.len      # ABI v2: lengths for the bounds checks
+    assert y.len == z.len == dst.len
+
+
+def test_cross_handle_buffers_are_recorded_as_used(stub):
+    """a column allocated through an upload handle and consumed on the compute handle: every op
+    tells the allocator (agpu_buffer_record_use) before it launches"""
+    lib, dev = stub
+    up = ag.GpuDevice(0)
+    a = ag.Int32ArrayGPU.from_slice([1] * 64, up)
+    b = ag.Int32ArrayGPU.from_slice([2] * 64, dev)
+    a.gpu_device = dev
+    a.add(b)
+    used = [args for n, args in lib.calls if n == "agpu_buffer_record_use"]
+    assert len(used) == 1 and used[0][1] == a.data.ptr and used[0][0] == dev.handle
+    names = [n for n, _a in lib.calls]
+    assert names.index("agpu_buffer_record_use") < names.index("agpu_binary")
+    up.handle = None
+
+
+def test_captured_pipeline_brackets_the_ops_with_graph_begin_and_end(stub):
+    lib, dev = stub
+    a, b = f32(dev), f32(dev)
+    p = ag.ArrowComputePipeline(dev, "prog", capture=True)
+    a.add_op(b, p)
+    a.gt_op(b, p)
+    p.finish()
+    p.replay()
+    names = [n for n, _a in lib.calls if n.startswith("agpu_graph") or n in LAUNCHING]
+    assert names == ["agpu_graph_begin", "agpu_binary", "agpu_compare", "agpu_graph_end", "agpu_graph_kernel_count",
+                     "agpu_graph_launch", "agpu_graph_launch"], names

@@ -117,3 +117,18 @@ def test_combine_partial_sums_is_a_rank_ordered_fold():
     assert sharded.combine_partial_sums(np.array([2**31 - 1, 1], dtype=np.int32), np.int32) == np.int32(-2**31)
     assert sharded.combine_partial_sums(np.array([2**32 - 1, 2], dtype=np.uint32), np.uint32) == np.uint32(1)
     assert sharded.combine_partial_sums(np.array([], dtype=np.float32), np.float32) == np.float32(0)
+
+
+def test_exchange_result_block_is_parsed_like_the_wait_kernel_writes_it():
+    """agpu_exchange_wait writes {offset of every rank, total, status, count of every rank}
+    (include/agpu.h); a non-zero status (a peer never posted) must raise, not return offsets"""
+    from arrow_gpu_b200 import sharded
+    from arrow_gpu_b200._ffi import AgpuError
+    counts = [7, 0, 5, 11]
+    offs, total = sharded.exclusive_offsets(counts)
+    words = offs + [total, 0] + counts
+    assert sharded.parse_exchange_result(words, 2, 4) == (offs, total, counts)
+    assert offs == [0, 7, 7, 12] and total == 23
+    words[5] = 1
+    with pytest.raises(AgpuError):
+        sharded.parse_exchange_result(words, 2, 4)
