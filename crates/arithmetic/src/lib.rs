@@ -362,3 +362,27 @@ pub fn neg_op_dyn(data: &ArrowArrayGPU, pipeline: &mut ArrowComputePipeline) -> 
         _ => panic!("Operation neg_dyn not supported for type {:?}", data.get_dtype()),
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// new surface (BASELINE.json config 3): the recorded chain  gt_op(add_op(mul_op(a, b), c), d)  of
+// crates/arrow/examples/simple.rs:45-72 as ONE kernel, bit-identical to the three ops (two
+// roundings, no FMA contraction); validity = AND of the four bitmaps
+// ---------------------------------------------------------------------------------------------
+pub fn fused_mul_add_gt_op(
+    a: &Float32ArrayGPU, b: &Float32ArrayGPU, c: &Float32ArrayGPU, d: &Float32ArrayGPU, _pipeline: &mut ArrowComputePipeline,
+) -> BooleanArrayGPU {
+    assert!(a.len == b.len && a.len == c.len && a.len == d.len, "fused_mul_add_gt_op: length mismatch");
+    let nb = NullBitBufferGpu::for_output(&a.gpu_device, a.len,
+                                          &[a.null_buffer.as_ref(), b.null_buffer.as_ref(), c.null_buffer.as_ref(), d.null_buffer.as_ref()]);
+    let out = BooleanArrayGPU::new_empty(&a.gpu_device, a.len, nb);
+    check(
+        unsafe {
+            agpu_fused_mul_add_gt(a.gpu_device.handle(), a.values_ptr() as *const f32, b.values_ptr() as *const f32,
+                                  c.values_ptr() as *const f32, d.values_ptr() as *const f32, out.data.ptr() as *mut u32, a.len,
+                                  a.validity_ptr(), b.validity_ptr(), c.validity_ptr(), d.validity_ptr(),
+                                  NullBitBufferGpu::words_mut(out.null_buffer.as_ref()))
+        },
+        "fused_mul_add_gt_op",
+    );
+    out
+}
