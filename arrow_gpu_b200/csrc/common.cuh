@@ -234,5 +234,35 @@ static inline size_t agpu_dtype_size(int dtype) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// count exchange between the GPUs of one box (exchange.cu; the filter's count kernel can post too)
+// ---------------------------------------------------------------------------------------------
+constexpr int kExchangeTagBits = 24;
+constexpr int kExchangeValueBits = 64 - kExchangeTagBits;  // 40: counts below 2^40 rows per shard
+constexpr unsigned long long kExchangeValueMask = (1ull << kExchangeValueBits) - 1ull;
+
+__host__ __device__ inline unsigned long long exchange_tag(uint32_t seq) {
+  return (unsigned long long)(seq % 0xFFFFFFu) + 1ull;  // never 0: a zeroed slot is "nothing posted"
+}
+
+struct ExchangePost {  // world == 0: nothing to post
+  unsigned long long* slots[AGPU_MAX_SHARDS];  // slot area of every rank as mapped into this process
+  int rank, world;
+  uint32_t seq;
+};
+
+#ifdef __CUDACC__
+// lane r < world of ONE warp stores {tag, value} into slot[rank] of rank r's area: one 64-bit word
+// carries tag AND value, so a relaxed system-scope store is enough (nothing else is published)
+__device__ __forceinline__ void exchange_post_lane(const ExchangePost& p, unsigned long long v, int r) {
+  if (r >= p.world) return;
+  if (v > kExchangeValueMask) v = kExchangeValueMask;  // cannot happen for row counts; keeps the tag intact
+  const unsigned long long word = (exchange_tag(p.seq) << kExchangeValueBits) | v;
+  unsigned long long* dst = p.slots[r] + (size_t)(p.seq % AGPU_EXCHANGE_RING) * p.world + p.rank;
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+}
+#endif
+
 // internal launchers shared between translation units
 int agpu_launch_bitmap_and(agpu_device* dev, const BmAnd& bm, size_t n_bits);
+int agpu_make_exchange_post(void* const* peer_slots, int rank, int world, uint32_t seq, ExchangePost* out);

@@ -19,28 +19,8 @@
 
 namespace {
 
-constexpr int kTagBits = 24;
-constexpr int kValueBits = 64 - kTagBits;  // 40: counts below 2^40 rows per shard
-constexpr unsigned long long kValueMask = (1ull << kValueBits) - 1ull;
-
-__host__ __device__ inline unsigned long long exchange_tag(uint32_t seq) {
-  return (unsigned long long)(seq % 0xFFFFFFu) + 1ull;  // never 0: a zeroed slot is "nothing posted"
-}
-
-struct PeerSlots {
-  unsigned long long* slots[AGPU_MAX_SHARDS];
-};
-
-__global__ void exchange_post_kernel(const unsigned long long* __restrict__ value, const PeerSlots peers, const int rank,
-                                     const int world, const uint32_t seq) {
-  const int r = threadIdx.x;
-  if (r >= world) return;
-  unsigned long long v = *value;
-  if (v > kValueMask) v = kValueMask;  // cannot happen for row counts (2^40 rows); keeps the tag intact
-  const unsigned long long word = (exchange_tag(seq) << kValueBits) | v;
-  unsigned long long* dst = peers.slots[r] + (size_t)(seq % AGPU_EXCHANGE_RING) * world + rank;
-  // relaxed is enough: the one word carries tag AND value, nothing else is published with it
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+__global__ void exchange_post_kernel(const unsigned long long* __restrict__ value, const ExchangePost post) {
+  exchange_post_lane(post, *value, threadIdx.x);
 }
 
 __global__ void exchange_wait_kernel(const unsigned long long* __restrict__ my_slots, const int world, const uint32_t seq,
@@ -56,7 +36,7 @@ __global__ void exchange_wait_kernel(const unsigned long long* __restrict__ my_s
     for (;;) {
       unsigned long long word;
       asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
-      if ((word >> kValueBits) == want) { v = word & kValueMask; break; }
+      if ((word >> kExchangeValueBits) == want) { v = word & kExchangeValueMask; break; }
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (now - t0 > timeout_ns) { ok = 0; break; }  // a peer died or skipped the exchange: report, never hang
       __nanosleep(64);
@@ -84,16 +64,28 @@ extern "C" size_t agpu_exchange_bytes(int world) {
   return ((size_t)AGPU_EXCHANGE_RING * world * 8 + 255) / 256 * 256;
 }
 
-extern "C" int agpu_exchange_post(agpu_device* dev, const uint64_t* value_dev, void* const* peer_slots, int rank,
-                                  int world, uint32_t seq) {
-  if (!dev) return AGPU_ENODEVICE;
-  if (!value_dev || !peer_slots || world < 1 || world > AGPU_MAX_SHARDS || rank < 0 || rank >= world) return AGPU_EINVAL;
-  PeerSlots p{};
+int agpu_make_exchange_post(void* const* peer_slots, int rank, int world, uint32_t seq, ExchangePost* out) {
+  if (!peer_slots || world < 1 || world > AGPU_MAX_SHARDS || rank < 0 || rank >= world) return AGPU_EINVAL;
+  ExchangePost p{};
   for (int r = 0; r < world; ++r) {
     if (!peer_slots[r]) return AGPU_EINVAL;
     p.slots[r] = (unsigned long long*)peer_slots[r];
   }
-  AGPU_LAUNCH(dev, exchange_post_kernel, 1, 32, 0, (const unsigned long long*)value_dev, p, rank, world, seq);
+  p.rank = rank;
+  p.world = world;
+  p.seq = seq;
+  *out = p;
+  return 0;
+}
+
+extern "C" int agpu_exchange_post(agpu_device* dev, const uint64_t* value_dev, void* const* peer_slots, int rank,
+                                  int world, uint32_t seq) {
+  if (!dev) return AGPU_ENODEVICE;
+  if (!value_dev) return AGPU_EINVAL;
+  ExchangePost p{};
+  const int rc = agpu_make_exchange_post(peer_slots, rank, world, seq, &p);
+  if (rc) return rc;
+  AGPU_LAUNCH(dev, exchange_post_kernel, 1, 32, 0, (const unsigned long long*)value_dev, p);
   return agpu_finish_launch();
 }
 

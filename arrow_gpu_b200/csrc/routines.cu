@@ -384,7 +384,8 @@ __global__ void __launch_bounds__(kBlock) filter_count_kernel(const uint32_t* __
                                                               const uint32_t* __restrict__ vmask, const size_t n,
                                                               uint32_t* __restrict__ counts,
                                                               uint64_t* group_totals, const int vec,
-                                                              unsigned int* ticket, unsigned long long* total) {
+                                                              unsigned int* ticket, unsigned long long* total,
+                                                              const ExchangePost post) {
   __shared__ uint32_t warp_tot[kBlock / 32];
   __shared__ bool is_last;
   const size_t nwords = (n + 31) / 32;
@@ -437,6 +438,10 @@ __global__ void __launch_bounds__(kBlock) filter_count_kernel(const uint32_t* __
   __threadfence();                                          // every other CTA's total is visible now
   scan_group_totals<kBlock>(group_totals, gridDim.x, total);
   if (threadIdx.x == 0) *ticket = 0u;
+  if (post.world) {  // sharded caller: this shard's total goes straight to every peer (agpu_filter_count_post)
+    __syncthreads();
+    if (threadIdx.x < 32) exchange_post_lane(post, __ldcg(total), threadIdx.x);
+  }
 }
 
 // store `val` at shared-memory byte address `sa` and advance `sa` by one element iff bit != 0
@@ -1140,22 +1145,37 @@ extern "C" size_t agpu_filter_scratch_bytes(size_t n) {
   return ((filter_groups(n) * 8 + 15) / 16) * 16 + ((filter_tiles(n) * 4 + 15) / 16) * 16 + 16;
 }
 
-extern "C" int agpu_filter_count(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n,
-                                 void* scratch, uint64_t* total_dev) {
+static int filter_count_impl(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n, void* scratch,
+                             uint64_t* total_dev, const ExchangePost& post) {
   if (!dev) return AGPU_ENODEVICE;
   if (!scratch || !total_dev || (n && !mask)) return AGPU_EINVAL;
-  if (n == 0) {
+  if (!dev->ticket) return AGPU_ENODEVICE;
+  // n == 0 still runs the kernel when there is something to post (one empty group: total = 0)
+  if (n == 0 && !post.world) {
     AGPU_CUDA(cudaMemsetAsync(total_dev, 0, 8, dev->stream));
     return 0;
   }
   const FilterScratch sc = filter_scratch(scratch, n);
-  const size_t groups = filter_groups(n);
+  const size_t groups = n ? filter_groups(n) : 1;
   if (groups > 0x7FFFFFFFull) return AGPU_EINVAL;
   const int vec = aligned16(mask) && (!vmask || aligned16(vmask));
-  if (!dev->ticket) return AGPU_ENODEVICE;
   AGPU_LAUNCH(dev, filter_count_kernel, (unsigned)groups, kBlock, 0, mask, vmask, n, sc.counts, sc.group_offsets, vec, dev->ticket,
-              (unsigned long long*)total_dev);
+              (unsigned long long*)total_dev, post);
   return agpu_finish_launch();
+}
+
+extern "C" int agpu_filter_count(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n,
+                                 void* scratch, uint64_t* total_dev) {
+  return filter_count_impl(dev, mask, vmask, n, scratch, total_dev, ExchangePost{});
+}
+
+extern "C" int agpu_filter_count_post(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n,
+                                      void* scratch, uint64_t* total_dev, void* const* peer_slots, int rank, int world,
+                                      uint32_t seq) {
+  ExchangePost post{};
+  const int rc = agpu_make_exchange_post(peer_slots, rank, world, seq, &post);
+  if (rc) return rc;
+  return filter_count_impl(dev, mask, vmask, n, scratch, total_dev, post);
 }
 
 extern "C" int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src, const uint32_t* vsrc,

@@ -559,9 +559,11 @@ class FilterPlan:
         self.array, self.mask, self.scratch, self.total = array, mask, scratch, total
 
 
-def _filter_count_op(self, mask, pipeline, total_ptr=None) -> FilterPlan:
+def _filter_count_op(self, mask, pipeline, total_ptr=None, post=None) -> FilterPlan:
     """first half of filter: count the selected rows (one pass over the mask bits).  `total_ptr`
-    may point at caller-owned device memory (8 bytes) that receives the count."""
+    may point at caller-owned device memory (8 bytes) that receives the count.  `post` =
+    (peer slot pointers, rank, world, seq) of a sharded.CountExchange: the count kernel itself then
+    stores this shard's total into every peer's slot area (agpu_filter_count_post)."""
     if not isinstance(mask, BooleanArrayGPU) or isinstance(self, BooleanArrayGPU):
         raise Panic(f"Filter Operation not supported for {self.get_dtype()}")
     _check_same_len(self, mask, "filter")
@@ -569,8 +571,13 @@ def _filter_count_op(self, mask, pipeline, total_ptr=None) -> FilterPlan:
     l = lib()
     scratch = dev.create_empty_buffer(l.agpu_filter_scratch_bytes(self.len))
     total = None if total_ptr is not None else dev.create_empty_buffer(8)
-    check(l.agpu_filter_count(dev.handle, mask.data.ptr, _vptr(mask.null_buffer), self.len, scratch.ptr,
-                              total_ptr if total_ptr is not None else total.ptr), "filter_count")
+    tptr = total_ptr if total_ptr is not None else total.ptr
+    if post is None:
+        check(l.agpu_filter_count(dev.handle, mask.data.ptr, _vptr(mask.null_buffer), self.len, scratch.ptr, tptr), "filter_count")
+    else:
+        ptrs, rank, world, seq = post
+        check(l.agpu_filter_count_post(dev.handle, mask.data.ptr, _vptr(mask.null_buffer), self.len, scratch.ptr, tptr, ptrs, rank,
+                                       world, seq), "filter_count_post")
     return FilterPlan(self, mask, scratch, total)
 
 

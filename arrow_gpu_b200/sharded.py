@@ -210,7 +210,7 @@ class PendingShardedFilter:
 
 def sharded_filter_async(array, mask, capacity=None, exchange="peer") -> PendingShardedFilter:
     """Enqueue a sharded filter without ANY host synchronisation:
-        count kernel -> post this shard's count to every peer -> scatter kernel -> wait for the peers
+        count kernel (its last CTA posts this shard's count to every peer) -> scatter kernel -> wait for the peers
     The output is sized for `capacity` rows (default: the shard's row count, always enough), so the
     scatter never waits for the count to reach the host.  exchange: "peer" = one 8-byte store per
     peer over NVLink + a polling kernel (CountExchange); "nccl" = all_gather_into_tensor on the same
@@ -237,8 +237,8 @@ def sharded_filter_async(array, mask, capacity=None, exchange="peer") -> Pending
         return pend
     if exchange == "peer":
         ex = count_exchange(dev)
-        plan = array.filter_count_op(mask, pipeline)
-        ex.post(plan.total.ptr)
+        # the count kernel posts the shard's total to every peer itself (its last CTA): no post launch
+        plan = array.filter_count_op(mask, pipeline, post=(ex.ptrs, ex.rank, ex.world, ex.seq))
         out = array.filter_scatter_op(plan, cap, pipeline)
         info = dev.create_empty_buffer((2 * world + 2) * 8)
         ex.wait(info.ptr)

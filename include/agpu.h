@@ -360,6 +360,11 @@ int agpu_exchange_post(agpu_device* dev, const uint64_t* value_dev, void* const*
                        int world, uint32_t seq);
 int agpu_exchange_wait(agpu_device* dev, const void* my_slots, int world, uint32_t seq,
                        uint64_t* out_dev, uint32_t timeout_ms);
+/* agpu_filter_count + agpu_exchange_post in one launch: the CTA of the count kernel that finishes
+ * last (it scans the group totals) also stores the shard's total into every peer's slot area. */
+int agpu_filter_count_post(agpu_device* dev, const uint32_t* mask, const uint32_t* vmask, size_t n,
+                           void* scratch, uint64_t* total_dev, void* const* peer_slots, int rank,
+                           int world, uint32_t seq);
 
 /* ---- "next" rows ---- */
 
