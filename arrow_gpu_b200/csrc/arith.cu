@@ -1,4 +1,6 @@
 // arith.cu — agpu_binary / agpu_scalar: arithmetic, min/max, bitwise logical and power.
+#include <stdlib.h>
+
 #include "elementwise.cuh"
 #include "ops.cuh"
 
@@ -13,7 +15,10 @@ int run_binary(agpu_device* dev, const void* a, const void* b, void* out, size_t
 template <template <typename> class F, typename T>
 int run_scalar(agpu_device* dev, const void* a, const void* s, void* out, size_t n, const BmAnd& bm) {
   ScalarOp<T, F<T>> op{(const T*)a, (const T*)s, (T*)out, F<T>{}};
-  return launch_ew(dev, op, n, bm, aligned16(a) && aligned16(out));
+  // 2 B/row ops (1-byte column, scalar rhs): 2 granules per thread measured 1 % faster than 4 and 2 %
+  // faster than 8 (84 us kernels; profiles/r02_persistent_ab.md)
+  constexpr int UNROLL = sizeof(T) == 1 ? 2 : 4;
+  return launch_ew<ScalarOp<T, F<T>>, UNROLL>(dev, op, n, bm, aligned16(a) && aligned16(out));
 }
 
 template <typename T>

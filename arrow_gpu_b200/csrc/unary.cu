@@ -1,4 +1,6 @@
 // unary.cu — agpu_unary: neg / abs / not, f32 math, trig (with the int->f32 cast fused).
+#include <stdlib.h>
+
 #include "elementwise.cuh"
 #include "ops.cuh"
 
@@ -7,7 +9,8 @@ namespace {
 template <typename TI, typename TO, class F>
 int run_unary(agpu_device* dev, const void* a, void* out, size_t n, const BmAnd& bm) {
   UnaryOp<TI, TO, F> op{(const TI*)a, (TO*)out, F{}};
-  return launch_ew(dev, op, n, bm, aligned16(a) && aligned16(out));
+  constexpr int UNROLL = (sizeof(TI) == 1 && sizeof(TO) == 1) ? 2 : 4;  // 2 B/row ops: see arith.cu run_scalar
+  return launch_ew<UnaryOp<TI, TO, F>, UNROLL>(dev, op, n, bm, aligned16(a) && aligned16(out));
 }
 
 // 8-bit column -> f32 function value.  An 8-bit input has 256 possible values, so each CTA
