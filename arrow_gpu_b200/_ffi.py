@@ -74,8 +74,6 @@ SIGNATURES = {
     "agpu_filter_scratch_bytes": (_sz, [_sz]),
     "agpu_filter_count": (_i, [_p, _u32p, _u32p, _sz, _p, _p]),
     "agpu_filter_count_post": (_i, [_p, _u32p, _u32p, _sz, _p, _p, C.POINTER(_p), _i, _i, C.c_uint32]),
-    "agpu_filter_onepass_scratch_bytes": (_sz, [_sz]),
-    "agpu_filter_onepass": (_i, [_p, _i, _p, _u32p, _u32p, _u32p, _sz, _p, _p, _u32p, _sz, _p, C.POINTER(_p), _i, _i, C.c_uint32]),
     "agpu_filter_scatter": (_i, [_p, _i, _p, _u32p, _u32p, _u32p, _sz, _p, _p, _u32p, _sz]),
     "agpu_ipc_alloc": (_i, [_p, _sz, C.POINTER(_p)]),
     "agpu_ipc_free": (_i, [_p, _p]),

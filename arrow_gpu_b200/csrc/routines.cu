@@ -444,68 +444,6 @@ __global__ void __launch_bounds__(kBlock) filter_count_kernel(const uint32_t* __
   }
 }
 
-// --------------------------------------------------------------------------------------------
-// single-pass placement: decoupled look-back over per-tile descriptors
-// --------------------------------------------------------------------------------------------
-// The two-call filter reads the selection bits twice (count pass, then scatter).  In the one-pass
-// form every scatter CTA publishes its tile's count as {AGGREGATE, count} as soon as it knows it,
-// then looks back over its predecessors' descriptors — 32 per step, one per lane — adding
-// aggregates until it meets an {INCLUSIVE PREFIX, sum}; that gives its output offset, and it
-// publishes its own inclusive prefix for its successors.  Tile ids are blockIdx.x: CTAs are
-// dispatched in index order, so every predecessor of a running CTA is running or finished (the
-// assumption CUB's single-pass scan makes); a 2 s timeout turns a broken assumption into an error
-// flag instead of a hang.  Descriptor: bits 63..62 = status, low 62 bits = value.
-constexpr unsigned long long kDescAgg = 1ull << 62, kDescPrefix = 2ull << 62, kDescValue = (1ull << 62) - 1ull;
-
-__device__ __forceinline__ void desc_store(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long desc_load(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// called by ONE warp; returns the number of rows kept by all tiles before `tile`
-__device__ __forceinline__ uint64_t tile_lookback(unsigned long long* desc, const size_t tile, const uint32_t count, const int lane,
-                                                  unsigned int* error) {
-  if (tile == 0) {
-    if (lane == 0) desc_store(desc, kDescPrefix | count);
-    return 0;
-  }
-  if (lane == 0) desc_store(desc + tile, kDescAgg | count);
-  uint64_t excl = 0;
-  long long base = (long long)tile - 1;  // lane l inspects tile base - l
-  unsigned long long t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    const long long idx = base - lane;
-    const unsigned long long d = idx >= 0 ? desc_load(desc + idx) : kDescPrefix;  // "tile -1": prefix 0
-    const unsigned ready = __ballot_sync(0xFFFFFFFFu, (d >> 62) != 0);
-    const unsigned pref = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
-    const int k = pref ? __ffs(pref) - 1 : 31;                      // nearest predecessor with an inclusive prefix
-    const unsigned need = k == 31 ? 0xFFFFFFFFu : ((2u << k) - 1u);  // lanes 0..k must have published
-    if ((ready & need) != need) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (now - t0 > 2000000000ull) {  // never expected: report instead of hanging the GPU.  The impossible
-        if (lane == 0) *error = 1u;      // prefix propagates to every successor and into the total
-        excl = kDescValue;
-        break;
-      }
-      continue;
-    }
-    unsigned long long v = lane <= k ? (d & kDescValue) : 0ull;
-#pragma unroll
-    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
-    excl += v;
-    if (pref) break;
-    base -= 32;
-  }
-  if (lane == 0) desc_store(desc + tile, kDescPrefix | (excl + count));
-  return excl;
-}
-
 // store `val` at shared-memory byte address `sa` and advance `sa` by one element iff bit != 0
 template <typename U>
 __device__ __forceinline__ void stage_if(uint32_t& sa, U val, uint32_t bit) {
@@ -545,17 +483,14 @@ __device__ __forceinline__ void stage_lanes(uint32_t& sa, const uint32_t (&w)[4]
 // One CTA compacts a "super tile" of M = 4/sizeof(U) count-tiles, i.e. always 16 KiB of rows
 // (4096 x 4-byte, 8192 x 2-byte or 16384 x 1-byte rows): the per-tile barriers and prefix sums are
 // amortised over the same number of bytes for every element width.
-template <typename U, bool HAS_V, int BLOCK, bool ONEPASS = false>
+template <typename U, bool HAS_V, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK) filter_scatter_kernel(const U* __restrict__ src,
                                                                 const uint32_t* __restrict__ vsrc,
                                                                 const uint32_t* __restrict__ mask,
                                                                 const uint32_t* __restrict__ vmask, const size_t n,
                                                                 const uint32_t* __restrict__ counts,
                                                                 const uint64_t* __restrict__ group_offsets,
-                                                                U* __restrict__ out, uint32_t* vout, const uint64_t cap,
-                                                                unsigned long long* desc = nullptr, unsigned int* error = nullptr,
-                                                                unsigned long long* total = nullptr,
-                                                                const ExchangePost post = ExchangePost{}) {
+                                                                U* __restrict__ out, uint32_t* vout, const uint64_t cap) {
   constexpr int G = 16 / sizeof(U);                   // rows per 16-byte granule
   constexpr int M = 4 / sizeof(U);                    // count-tiles per super tile
   constexpr int ROWS = kFilterTileRows * M;           // rows per super tile (16 KiB of rows)
@@ -586,7 +521,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
   }
   uint32_t before = 0;
   uint64_t goff = 0;
-  if (!ONEPASS && warp == 1) {  // warp 1: output offset = group offset + counts of the earlier tiles of the group
+  if (warp == 1) {  // warp 1: output offset = group offset + counts of the earlier tiles of the group
     const size_t t0 = tile * M;  // first count-tile of this super tile (M divides the group size)
     const size_t gstart = t0 / kFilterGroupTiles * kFilterGroupTiles;
     if (gstart + lane < t0) before += counts[gstart + lane];
@@ -594,7 +529,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
     if (lane == 0) goff = group_offsets[t0 / kFilterGroupTiles];
   }
   for (int w = threadIdx.x; w < WORDS; w += BLOCK) sel[w] = sel_word(mask, vmask, w0 + w, nwords, n);
-  if (!ONEPASS && warp == 1) {
+  if (warp == 1) {
 #pragma unroll
     for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
     if (lane == 0) off_s = goff + before;
@@ -616,19 +551,6 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
     if (lane == 31) count_s = incl;
   }
   __syncthreads();
-  if constexpr (ONEPASS) {
-    // publish this tile's count, look back for its output offset (the rows requested above are in
-    // flight meanwhile); the last tile also knows the grand total
-    if (warp == 1) {
-      const uint64_t excl = tile_lookback(desc, tile, count_s, lane, error);
-      if (lane == 0) off_s = excl;
-      if (tile == gridDim.x - 1) {
-        if (lane == 0) *total = excl + count_s;
-        if (post.world) exchange_post_lane(post, excl + count_s, lane);
-      }
-    }
-    __syncthreads();
-  }
   const uint64_t off = off_s;
   // rows past the capacity of the output buffers are dropped (a caller that sized the output from
   // a selectivity estimate learns the real total from the count pass and retries)
@@ -822,8 +744,7 @@ __global__ void __launch_bounds__(kBitsBlock) filter_bits_kernel(const uint32_t*
                                                                  const uint32_t* __restrict__ vmask, const size_t n,
                                                                  const uint32_t* __restrict__ counts,
                                                                  const uint64_t* __restrict__ group_offsets,
-                                                                 uint32_t* vout, const uint64_t cap, const int vec,
-                                                                 const unsigned long long* __restrict__ desc, const int desc_rows) {
+                                                                 uint32_t* vout, const uint64_t cap, const int vec) {
   __shared__ uint32_t warp_tot[kBitsBlock / 32];
   __shared__ uint64_t off_s;
   const size_t nwords = (n + 31) / 32;
@@ -851,12 +772,7 @@ __global__ void __launch_bounds__(kBitsBlock) filter_bits_kernel(const uint32_t*
       val[k] = w0 + k < nwords ? vsrc[w0 + k] : 0u;
     }
   }
-  if (desc) {  // after a one-pass scatter: the inclusive prefix of the tile before this CTA's first row
-    if (threadIdx.x == 32) {
-      const size_t d0 = (size_t)blockIdx.x * (size_t)(kBitsCtaWords * 32 / desc_rows);
-      off_s = d0 ? (desc[d0 - 1] & kDescValue) : 0ull;
-    }
-  } else if (warp == 1) {  // output offset of this CTA's first row: group offset + counts of the earlier tiles of the group
+  if (warp == 1) {  // output offset of this CTA's first row: group offset + counts of the earlier tiles of the group
     const size_t t0 = (size_t)blockIdx.x * kBitsTilesPerCta;
     const size_t gstart = t0 / kFilterGroupTiles * kFilterGroupTiles;
     uint32_t before = 0;
@@ -1149,7 +1065,7 @@ int run_filter(agpu_device* dev, const void* src, const uint32_t* vsrc, const ui
     const size_t bit_ctas = ceil_div(ceil_div(n, (size_t)32), (size_t)kBitsCtaWords);
     const int vec = aligned16(vsrc) && aligned16(mask) && (!vmask || aligned16(vmask));
     AGPU_LAUNCH(dev, filter_bits_kernel, (unsigned)bit_ctas, kBitsBlock, 0, vsrc, mask, vmask, n, sc.counts,
-                sc.group_offsets, vout, (uint64_t)cap, vec, (const unsigned long long*)nullptr, 0);
+                sc.group_offsets, vout, (uint64_t)cap, vec);
   }
   // (1- and 2-byte rows: a word-level scatter — 64 contiguous bytes per thread, table-driven prmt
   // compaction of two packed words at a time, whole-word stores — was built and measured SLOWER than
@@ -1274,66 +1190,6 @@ extern "C" int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src,
     case 4: return run_filter<uint32_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout, out_capacity);
     case 2: return run_filter<uint16_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout, out_capacity);
     case 1: return run_filter<uint8_t>(dev, src, vsrc, mask, vmask, n, sc, out, vout, out_capacity);
-    default: return AGPU_EUNSUPPORTED;
-  }
-}
-
-// ---- single-pass filter ----
-struct OnePassScratch {
-  unsigned int* error;       // [0]: look-back timed out (never expected)
-  unsigned long long* desc;  // one descriptor per scatter CTA
-};
-static inline OnePassScratch onepass_scratch(void* p) {
-  return OnePassScratch{(unsigned int*)p, (unsigned long long*)((char*)p + 16)};
-}
-
-extern "C" size_t agpu_filter_onepass_scratch_bytes(size_t n) { return 16 + filter_tiles(n) * 8 + 16; }
-
-template <typename U>
-static int run_filter_onepass(agpu_device* dev, const void* src, const uint32_t* vsrc, const uint32_t* mask, const uint32_t* vmask,
-                              size_t n, void* scratch, void* out, uint32_t* vout, size_t cap, uint64_t* total_dev,
-                              const ExchangePost& post) {
-  constexpr int BLOCK = 256;
-  constexpr size_t kRows = (size_t)kFilterTileRows * (4 / sizeof(U));  // rows per scatter CTA (16 KiB of rows)
-  const size_t ctas = ceil_div(n, kRows);
-  if (ctas > 0x7FFFFFFFull) return AGPU_EINVAL;
-  if (!aligned16(src)) return AGPU_EINVAL;
-  const OnePassScratch sc = onepass_scratch(scratch);
-  AGPU_CUDA(cudaMemsetAsync(scratch, 0, 16 + ctas * 8, dev->stream));  // descriptors start as "nothing published"
-  AGPU_LAUNCH(dev, (filter_scatter_kernel<U, false, BLOCK, true>), (unsigned)ctas, BLOCK, 0, (const U*)src, vsrc, mask, vmask, n,
-              (const uint32_t*)nullptr, (const uint64_t*)nullptr, (U*)out, vout, (uint64_t)cap, sc.desc, sc.error,
-              (unsigned long long*)total_dev, post);
-  if (vsrc && vout) {  // validity of the kept rows: bitmap-only pass, tile offsets = the descriptors' inclusive prefixes
-    AGPU_CUDA(cudaMemsetAsync(vout, 0, ((cap + 31) / 32) * 4, dev->stream));
-    const size_t bit_ctas = ceil_div(ceil_div(n, (size_t)32), (size_t)kBitsCtaWords);
-    const int vec = aligned16(vsrc) && aligned16(mask) && (!vmask || aligned16(vmask));
-    AGPU_LAUNCH(dev, filter_bits_kernel, (unsigned)bit_ctas, kBitsBlock, 0, vsrc, mask, vmask, n, (const uint32_t*)nullptr,
-                (const uint64_t*)nullptr, vout, (uint64_t)cap, vec, (const unsigned long long*)sc.desc, (int)kRows);
-  }
-  return agpu_finish_launch();
-}
-
-extern "C" int agpu_filter_onepass(agpu_device* dev, int dtype, const void* src, const uint32_t* vsrc, const uint32_t* mask,
-                                   const uint32_t* vmask, size_t n, void* scratch, void* out, uint32_t* vout,
-                                   size_t out_capacity, uint64_t* total_dev, void* const* peer_slots, int rank, int world,
-                                   uint32_t seq) {
-  if (!dev) return AGPU_ENODEVICE;
-  if (!scratch || !total_dev || (n && (!src || !mask))) return AGPU_EINVAL;
-  ExchangePost post{};
-  if (peer_slots) {
-    const int rc = agpu_make_exchange_post(peer_slots, rank, world, seq, &post);
-    if (rc) return rc;
-  }
-  if (n == 0) {  // nothing to scan: total = 0 (and the peers still get this shard's post)
-    AGPU_CUDA(cudaMemsetAsync(total_dev, 0, 8, dev->stream));
-    if (post.world) return agpu_exchange_post(dev, total_dev, peer_slots, rank, world, seq);
-    return 0;
-  }
-  if (!out && out_capacity) return AGPU_EINVAL;
-  switch (agpu_dtype_size(dtype)) {
-    case 4: return run_filter_onepass<uint32_t>(dev, src, vsrc, mask, vmask, n, scratch, out, vout, out_capacity, total_dev, post);
-    case 2: return run_filter_onepass<uint16_t>(dev, src, vsrc, mask, vmask, n, scratch, out, vout, out_capacity, total_dev, post);
-    case 1: return run_filter_onepass<uint8_t>(dev, src, vsrc, mask, vmask, n, scratch, out, vout, out_capacity, total_dev, post);
     default: return AGPU_EUNSUPPORTED;
   }
 }

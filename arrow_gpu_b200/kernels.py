@@ -598,32 +598,6 @@ def _filter_scatter_op(self, plan: FilterPlan, count: int, pipeline):
     return out
 
 
-def _filter_onepass_op(self, mask, capacity, pipeline, post=None):
-    """filter in ONE kernel (agpu_filter_onepass): tiles are placed by a decoupled look-back, so the
-    selection bits are read once and nothing has to be known before the launch — except the size of
-    the output, which is `capacity` rows (the array's length is always enough).  Returns
-    (array of `capacity` rows holding the kept rows first, device buffer with the u64 row count).
-    `post` = (peer slot pointers, rank, world, seq): the kernel also posts the count to the peers."""
-    if not isinstance(mask, BooleanArrayGPU) or isinstance(self, BooleanArrayGPU):
-        raise Panic(f"Filter Operation not supported for {self.get_dtype()}")
-    _check_same_len(self, mask, "filter")
-    dev = self.gpu_device
-    l = lib()
-    _note_foreign_buffers(dev, (self, mask))
-    scratch = dev.create_empty_buffer(l.agpu_filter_onepass_scratch_bytes(self.len))
-    total = dev.create_empty_buffer(8)
-    out = type(self).empty(capacity, dev)
-    vout = None
-    if self.null_buffer is not None:
-        vout = dev.create_empty_buffer(bitmap_words(capacity) * 4)
-        out.null_buffer = NullBitBufferGpu(vout, capacity, dev)
-    ptrs, rank, world, seq = post if post is not None else (None, 0, 0, 0)
-    check(l.agpu_filter_onepass(dev.handle, self.DTYPE, self.data.ptr, _vptr(self.null_buffer), mask.data.ptr,
-                                _vptr(mask.null_buffer), self.len, scratch.ptr, out.data.ptr, vout.ptr if vout else None,
-                                capacity, total.ptr, ptrs, rank, world, seq), "filter_onepass")
-    return out, total
-
-
 def _filter_op(self, mask, pipeline):
     """New surface (BASELINE.json config 5; the reference has no filter): keep rows whose mask
     bit is set and valid, order preserving.  Needs the selected count on the host to size the
@@ -642,7 +616,6 @@ for _cls in (PrimitiveArrayGpu, BooleanArrayGPU):
     _cls.put = _eager(_put_op)
 PrimitiveArrayGpu.filter_op = _filter_op
 PrimitiveArrayGpu.filter = _eager(_filter_op)
-PrimitiveArrayGpu.filter_onepass_op = _filter_onepass_op
 PrimitiveArrayGpu.filter_count_op = _filter_count_op
 PrimitiveArrayGpu.filter_scatter_op = _filter_scatter_op
 

@@ -173,8 +173,8 @@ class PendingShardedFilter:
     has synchronised with the host yet; `result()` does, once, and returns what `sharded_filter`
     returns.  Dependent device work can be enqueued before calling it."""
 
-    def __init__(self, array, mask, out, capacity, info, info_kind, rank, world, gathered=None):
-        self.array, self.mask, self.out, self.capacity = array, mask, out, capacity
+    def __init__(self, array, plan, out, capacity, info, info_kind, rank, world, gathered=None):
+        self.array, self.plan, self.out, self.capacity = array, plan, out, capacity
         self.info, self.info_kind, self.rank, self.world, self.gathered = info, info_kind, rank, world, gathered
         self._resolved = None
 
@@ -182,7 +182,6 @@ class PendingShardedFilter:
         if self._resolved is not None:
             return self._resolved
         import numpy as np
-        from ._ffi import AgpuError
         from .array import NullBitBufferGpu
         dev = self.array.gpu_device
         if self.info_kind == "peer":
@@ -193,31 +192,29 @@ class PendingShardedFilter:
             with torch.cuda.stream(self.info):
                 counts = self.gathered.cpu().tolist()      # one synchronisation, after everything was enqueued
             offsets, total = exclusive_offsets(counts)
-        else:                                              # single shard: the kernel's total
+        else:                                              # single shard: the count pass's total
             counts = [int(_read_small(dev, self.info, 8).view(np.uint64)[0])]
             offsets, total = [0], counts[0]
         count = int(counts[self.rank])
-        if count > self.array.len:                         # the look-back of the one-pass kernel gave up (never expected)
-            raise AgpuError(-5, "agpu_filter_onepass (look-back timeout)")
         out = self.out
-        if count > self.capacity:      # the estimate was too small: redo with the exact size (count pass + scatter)
-            out = self.array.filter(self.mask)
+        if count > self.capacity:      # the estimate was too small: redo the scatter with the exact size
+            out = self.array.filter_scatter_op(self.plan, count, None)
         nb = None
         if out.null_buffer is not None:
             nb = NullBitBufferGpu(out.null_buffer.bit_buffer, count, dev)
         final = type(out)(out.data, dev, count, nb)
         self._resolved = (final, int(offsets[self.rank]), int(total))
-        self.mask = self.out = None
+        self.plan = self.out = None
         return self._resolved
 
 
 def sharded_filter_async(array, mask, capacity=None, exchange="peer") -> PendingShardedFilter:
     """Enqueue a sharded filter without ANY host synchronisation:
-        one-pass filter kernel (places its tiles by look-back, posts this shard's count to every peer) -> wait for the peers
-    The output is sized for `capacity` rows (default: the shard's row count, always enough), so
-    nothing waits for a count to reach the host.  exchange: "peer" = one 8-byte store per peer over
-    NVLink + a polling kernel (CountExchange); "nccl" = count pass, all_gather_into_tensor on the
-    same stream, scatter (kept for comparison)."""
+        count kernel (its last CTA posts this shard's count to every peer) -> scatter kernel -> wait for the peers
+    The output is sized for `capacity` rows (default: the shard's row count, always enough), so the
+    scatter never waits for the count to reach the host.  exchange: "peer" = one 8-byte store per
+    peer over NVLink + a polling kernel (CountExchange); "nccl" = all_gather_into_tensor on the same
+    stream (kept for comparison)."""
     from .array import ArrowComputePipeline
     dist = _dist()
     dev = array.gpu_device
@@ -226,27 +223,27 @@ def sharded_filter_async(array, mask, capacity=None, exchange="peer") -> Pending
     cap = array.len if capacity is None else min(int(capacity), array.len)
     pipeline = ArrowComputePipeline(dev, "sharded_filter")
     if dist is None or dist.get_backend() != "nccl":
-        out, total_buf = array.filter_onepass_op(mask, cap, pipeline)
+        plan = array.filter_count_op(mask, pipeline)
+        out = array.filter_scatter_op(plan, cap, pipeline)
         pipeline.finish()
         if dist is None:
-            return PendingShardedFilter(array, mask, out, cap, total_buf, "local", rank, world)
+            return PendingShardedFilter(array, plan, out, cap, plan.total, "local", rank, world)
         # CPU/gloo process groups (host-logic tests): counts travel through the host
         import numpy as np
-        count = int(dev.retrive_data(total_buf, 8).view(np.uint64)[0])
+        count = int(dev.retrive_data(plan.total, 8).view(np.uint64)[0])
         offsets, total = exchange_counts(count)
-        pend = PendingShardedFilter(array, mask, out, cap, None, "host", rank, world)
+        pend = PendingShardedFilter(array, plan, out, cap, None, "host", rank, world)
         pend._resolved = (type(out)(out.data, dev, count, out.null_buffer), offsets[rank], total)
         return pend
     if exchange == "peer":
         ex = count_exchange(dev)
-        # the kernel's last tile posts the shard's total to every peer itself: no count pass, no post launch
-        out, _total = array.filter_onepass_op(mask, cap, pipeline, post=(ex.ptrs, ex.rank, ex.world, ex.seq))
+        # the count kernel posts the shard's total to every peer itself (its last CTA): no post launch
+        plan = array.filter_count_op(mask, pipeline, post=(ex.ptrs, ex.rank, ex.world, ex.seq))
+        out = array.filter_scatter_op(plan, cap, pipeline)
         info = dev.create_empty_buffer((2 * world + 2) * 8)
         ex.wait(info.ptr)
         pipeline.finish()
-        pend = PendingShardedFilter(array, mask, out, cap, info, "peer", rank, world)
-        pend._keep = _total
-        return pend
+        return PendingShardedFilter(array, plan, out, cap, info, "peer", rank, world)
     import torch
     ctx = _EXCHANGE_CTX.get(id(dev))
     if ctx is None:   # per device handle: its stream as a torch stream
@@ -262,8 +259,8 @@ def sharded_filter_async(array, mask, capacity=None, exchange="peer") -> Pending
         dist.all_gather_into_tensor(gathered, mine)
         out = array.filter_scatter_op(plan, cap, pipeline)
         pipeline.finish()
-    pend = PendingShardedFilter(array, mask, out, cap, ext, "nccl", rank, world, gathered=gathered)
-    pend._keep = (mine, plan)
+    pend = PendingShardedFilter(array, plan, out, cap, ext, "nccl", rank, world, gathered=gathered)
+    pend._keep = mine
     return pend
 
 
@@ -271,7 +268,7 @@ def sharded_filter(array, mask, capacity=None, exchange="peer"):
     """Filter this rank's shard and learn where its output sits in the global result:
     returns (local filtered array, global offset of its first row, global row count).
 
-    The filter kernel and the count exchange are enqueued before the host looks at anything
+    All kernels of the filter AND the count exchange are enqueued before the host looks at anything
     (sharded_filter_async); the single synchronisation is the final read of the 8*(2*world+2)-byte
     result block.  Round 1 synchronised between the count and the scatter pass (all_gather +
     readback + stream sync), which left the GPU idle for a host round trip per filter."""

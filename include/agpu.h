@@ -340,19 +340,6 @@ int agpu_filter_scatter(agpu_device* dev, int dtype, const void* src, const uint
                         const uint32_t* mask, const uint32_t* vmask, size_t n, void* scratch,
                         void* out, uint32_t* vout, size_t out_capacity);
 
-/* Single-pass form: ONE kernel reads the selection bits and the rows once, places every tile with a
- * decoupled look-back over per-tile descriptors (no count pass), writes the total to *total_dev when
- * the last tile is placed and, if peer_slots != NULL, posts it to every peer like
- * agpu_exchange_post.  The output cannot be sized from the count, so the caller passes
- * `out_capacity` (rows past it are dropped; `n` is always enough) — the form a sharded or otherwise
- * asynchronous caller wants.  scratch: agpu_filter_onepass_scratch_bytes(n) bytes; its first word
- * is non-zero afterwards iff the look-back timed out (never expected; results are then invalid). */
-size_t agpu_filter_onepass_scratch_bytes(size_t n);
-int agpu_filter_onepass(agpu_device* dev, int dtype, const void* src, const uint32_t* vsrc,
-                        const uint32_t* mask, const uint32_t* vmask, size_t n, void* scratch, void* out,
-                        uint32_t* vout, size_t out_capacity, uint64_t* total_dev,
-                        void* const* peer_slots, int rank, int world, uint32_t seq);
-
 /* ---- count / offset exchange between the shards of one box, device side (north_star (4)) ----
  * Every rank (one process per GPU) owns a slot area of agpu_exchange_bytes(world) bytes in
  * agpu_ipc_alloc memory, zeroed once, exported with agpu_ipc_export and opened by every peer.

@@ -46,16 +46,4 @@ for name, cls, tdt, with_v, bpr in (("i8", ag.Int8ArrayGPU, torch.int8, False, 1
     if not ts:
         continue
     print(f"{name:14s} filter s=0.5: min {min(ts):.4f} ms  {bpr * n / min(ts) / 1e6:7.1f} GB/s  frac {bpr * n / min(ts) / 1e6 / 6541.1:.3f}  rows out {out.len}")
-    # the one-pass form (no count pass, no host synchronisation inside the timed region)
-    from arrow_gpu_b200 import sharded
-    ts = []
-    for _ in range(reps):
-        e0 = dev.record_event()
-        pend = sharded.sharded_filter_async(col, mask)
-        e1 = dev.record_event()
-        dev.sync()
-        ts.append(e0.elapsed_ms(e1))
-        del pend
-    if ts:
-        print(f"{name:14s} one-pass      min {min(ts):.4f} ms  {bpr * n / min(ts) / 1e6:7.1f} GB/s  frac {bpr * n / min(ts) / 1e6 / 6541.1:.3f}")
     del t, col, out

@@ -185,55 +185,3 @@ def test_out_of_memory_releases_the_caches_of_every_handle(device):
     lib.agpu_trim(other.handle)
     device.sync()
     other.sync()
-
-
-@pytest.mark.parametrize("dtype", WIDTHS, ids=lambda d: NAMES[d])
-def test_filter_onepass(dtype, device):
-    """agpu_filter_onepass (decoupled look-back, no count pass) = the two-call filter = the oracle,
-    for every width, ragged sizes around the tile boundaries, all selectivities, with and without
-    nulls; several thousand tiles so that the look-back really chains"""
-    from arrow_gpu_b200 import sharded
-    rng = np.random.default_rng(59 + dtype)
-    for n in SIZES + [4096 * 3, 4096 * 3 + 1, 16384 * 5 + 7, 1_000_003, 9_000_001]:
-        for sel in ((0.0, 0.1, 0.5, 0.9, 1.0) if n < 2_000_000 else (0.3,)):
-            for nulls, mnulls in ((False, False), (True, True)):
-                a, oa = make(rng, dtype, n, nulls, device)
-                m, om = make_bool(rng, n, mnulls, device, p=sel)
-                got, off, tot = sharded.sharded_filter_async(a, m).result()
-                want = oracle_filter(oa, om)
-                assert off == 0 and tot == want.n
-                assert_same(got, want, f"onepass filter {NAMES[dtype]} n={n} sel={sel} nulls={nulls}")
-
-
-def test_filter_onepass_capacity_and_total(device):
-    """rows past the capacity are dropped (nothing is written behind it), the total is exact"""
-    import ctypes as C
-    from arrow_gpu_b200 import _ffi
-    lib = _ffi.lib()
-    n = 300_007
-    rng = np.random.default_rng(61)
-    vals = rng.integers(-2**31, 2**31, n, dtype=np.int64).astype(np.int32)
-    valid = rng.random(n) < 0.9
-    keep = rng.random(n) < 0.5
-    a = ag.Int32ArrayGPU.from_numpy(vals, valid, device)
-    m = ag.BooleanArrayGPU.from_numpy(keep, None, device)
-    total = int(keep.sum())
-    for cap in (n, total, total - 1, 4096 * 5 + 3, 1):
-        guard = 1024
-        out = device.create_gpu_buffer_with_data(np.full(cap + guard, 0x5A5A5A5A, dtype=np.uint32))
-        vwords = (cap + 31) // 32
-        vout = device.create_gpu_buffer_with_data(np.full(vwords + guard, 0xFFFFFFFF, dtype=np.uint32))
-        scratch = device.create_empty_buffer(lib.agpu_filter_onepass_scratch_bytes(n))
-        tot = device.create_empty_buffer(8)
-        _ffi.check(lib.agpu_filter_onepass(device.handle, a.DTYPE, a.data.ptr, a.null_buffer.bit_buffer.ptr, m.data.ptr, None, n,
-                                           scratch.ptr, out.ptr, vout.ptr, cap, tot.ptr, None, 0, 0, 0), "filter_onepass")
-        assert int(device.retrive_data(tot, 8).view(np.uint64)[0]) == total
-        assert int(device.retrive_data(scratch, 4).view(np.uint32)[0]) == 0      # no look-back timeout
-        got = device.retrive_data(out).view(np.int32)
-        k = min(cap, total)
-        assert np.array_equal(got[:k], vals[keep][:k]), cap
-        assert np.all(got[cap:].view(np.uint32) == 0x5A5A5A5A), f"cap={cap}: wrote past the capacity"
-        gv = device.retrive_data(vout).view(np.uint32)
-        assert np.all(gv[vwords:] == 0xFFFFFFFF), cap
-        bits = O.unpack_bits(gv[:vwords].copy(), vwords * 32)
-        assert np.array_equal(bits[:k], valid[keep][:k]) and not bits[k:].any(), cap
