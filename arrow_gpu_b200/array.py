@@ -22,6 +22,8 @@ import numpy as np
 from . import _ffi
 from ._ffi import check, lib
 
+_byref = C.byref
+
 
 class ArrowErrorGPU(Exception):
     """crates/array/src/lib.rs:10-13"""
@@ -99,7 +101,9 @@ class GpuDevice:
     def create_empty_buffer(self, size: int) -> "ArrowGpuBuffer":
         """gpu_device.rs:183-192 (not zero-filled: every kernel writes its whole output)"""
         p = C.c_void_p()
-        check(lib().agpu_alloc(self.handle, _round_up(max(size, 1), 16), C.byref(p)), "agpu_alloc")
+        rc = (_ffi._lib or lib()).agpu_alloc(self.handle, (size + 15) & -16 or 16, _byref(p))   # hot: one call per output
+        if rc:
+            check(rc, "agpu_alloc")
         return ArrowGpuBuffer(self, p.value, size)
 
     def create_gpu_buffer_with_data(self, data: np.ndarray, wait: bool = True) -> "ArrowGpuBuffer":
@@ -260,7 +264,7 @@ class ArrowGpuBuffer:
                 elif self._kind == "peer":
                     lib().agpu_ipc_close(self.device.handle, self.ptr)
                 else:
-                    lib().agpu_free(self.device.handle, self.ptr)
+                    (_ffi._lib or lib()).agpu_free(self.device.handle, self.ptr)
         except Exception:
             pass
         self.ptr = None
@@ -501,9 +505,10 @@ def _vptr(nb: Optional[NullBitBufferGpu]):
 
 def _new_validity(dev: GpuDevice, length: int, *inputs: Optional[NullBitBufferGpu]):
     """Allocate the output bitmap of an op iff at least one input has one."""
-    if all(x is None for x in inputs):
-        return None
-    return NullBitBufferGpu(dev.create_empty_buffer(bitmap_words(length) * 4), length, dev)
+    for x in inputs:
+        if x is not None:
+            return NullBitBufferGpu(dev.create_empty_buffer(((length + 31) >> 5) * 4), length, dev)
+    return None
 
 
 # ------------------------------------------------------------------------------------------
@@ -515,6 +520,7 @@ class PrimitiveArrayGpu:
 
     DTYPE: int = -1                 # agpu dtype id
     NP: np.dtype = np.dtype("u1")   # numpy element type
+    ITEMSIZE: int = 1               # bytes per row
     ARROW_TYPE: ArrowType
 
     def __init__(self, data: ArrowGpuBuffer, gpu_device: GpuDevice, length: int,
@@ -627,7 +633,8 @@ class PrimitiveArrayGpu:
 
 
 def _prim(name: str, dtype: int, np_dtype: str, arrow_type: ArrowType):
-    return type(name, (PrimitiveArrayGpu,), {"DTYPE": dtype, "NP": np.dtype(np_dtype), "ARROW_TYPE": arrow_type})
+    return type(name, (PrimitiveArrayGpu,), {"DTYPE": dtype, "NP": np.dtype(np_dtype), "ARROW_TYPE": arrow_type,
+                                             "ITEMSIZE": np.dtype(np_dtype).itemsize})
 
 
 Float32ArrayGPU = _prim("Float32ArrayGPU", _ffi.F32, "<f4", ArrowType.Float32Type)

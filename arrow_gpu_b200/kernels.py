@@ -29,12 +29,18 @@ def _pipeline_for(arr) -> ArrowComputePipeline:
 
 
 def _eager(op_fn):
-    """default_impl! of the reference: new pipeline -> *_op -> finish"""
+    """default_impl! of the reference: new pipeline -> *_op -> finish.  The pipeline of an eager
+    call records nothing (ops enqueue on the stream at once), so one plain pipeline per device
+    handle serves every eager call instead of a new object per op."""
     def run(self, *args):
-        pipeline = _pipeline_for(self)
-        _note_foreign_buffers(self.gpu_device, (self,) + args)
+        dev = self.gpu_device
+        pipeline = getattr(dev, "_eager_pipeline", None)
+        if pipeline is None:
+            pipeline = dev._eager_pipeline = ArrowComputePipeline(dev, None)
+        _note_foreign_buffers(dev, (self,) + args)
         out = op_fn(self, *args, pipeline)
-        pipeline.finish()
+        if pipeline._lazies:
+            pipeline.flush_recorded()
         return out
     return run
 
@@ -45,59 +51,99 @@ def _check_same_len(a, b, what):
 
 
 # ==========================================================================================
-# low-level launchers (one C-ABI call each)
+# low-level launchers (one C-ABI call each).  These run once per op on columns of any size, so
+# they touch the private fields directly (after launching a pending recorded chain) and call the
+# library without the checking helper on the success path: ~5 us of interpreter time per op is
+# the whole cost of a 1 Mi-row column op (BASELINE.json configs[0]).
 # ==========================================================================================
+def _ready(x):
+    if x._lazy is not None:
+        x._materialize()
+
+
+def _alloc_validity(dev, n, va, vb=None):
+    """output bitmap iff an input has one (null_bit_buffer.rs:168-204) -> (NullBitBufferGpu | None, ptr | None)"""
+    if va is None and vb is None:
+        return None, None
+    buf = dev.create_empty_buffer(((n + 31) >> 5) * 4)
+    return NullBitBufferGpu(buf, n, dev), buf.ptr
+
+
 def _binary(op: int, a: PrimitiveArrayGpu, b: PrimitiveArrayGpu, out_cls=None, what="binary"):
-    _check_same_len(a, b, what)
-    dev = a.gpu_device
+    n = a.len
+    if n != b.len:
+        raise Panic(f"{what}: length mismatch {n} vs {b.len}")
+    _ready(a), _ready(b)
+    dev, va, vb = a.gpu_device, a._null_buffer, b._null_buffer
     out_cls = out_cls or type(a)
-    nb = _new_validity(dev, a.len, a.null_buffer, b.null_buffer)
-    out = out_cls.empty(a.len, dev, nb)
-    check(lib().agpu_binary(dev.handle, op, a.DTYPE, a.data.ptr, b.data.ptr, out.data.ptr, a.len,
-                            _vptr(a.null_buffer), _vptr(b.null_buffer), _vptr(nb)), what)
-    return out
+    nb, vout = _alloc_validity(dev, n, va, vb)
+    data = dev.create_empty_buffer(n * out_cls.ITEMSIZE)
+    rc = (_ffi._lib or lib()).agpu_binary(dev.handle, op, a.DTYPE, a._data.ptr, b._data.ptr, data.ptr, n,
+                                           va.bit_buffer.ptr if va is not None else None,
+                                           vb.bit_buffer.ptr if vb is not None else None, vout)
+    if rc:
+        check(rc, what)
+    return out_cls(data, dev, n, nb)
 
 
 def _scalar(op: int, a: PrimitiveArrayGpu, s: PrimitiveArrayGpu, what="scalar"):
     """rhs is a 1-element array; validity of `a` is copied (arithmetic/src/lib.rs:35-38)"""
     if s.len != 1:
         raise Panic(f"{what}: scalar operand must have exactly one element")
-    dev = a.gpu_device
-    nb = _new_validity(dev, a.len, a.null_buffer)
-    out = type(a).empty(a.len, dev, nb)
-    check(lib().agpu_scalar(dev.handle, op, a.DTYPE, a.data.ptr, s.data.ptr, out.data.ptr, a.len,
-                            _vptr(a.null_buffer), _vptr(nb)), what)
-    return out
+    _ready(a), _ready(s)
+    dev, n, va = a.gpu_device, a.len, a._null_buffer
+    nb, vout = _alloc_validity(dev, n, va)
+    data = dev.create_empty_buffer(n * a.ITEMSIZE)
+    rc = (_ffi._lib or lib()).agpu_scalar(dev.handle, op, a.DTYPE, a._data.ptr, s._data.ptr, data.ptr, n,
+                                           va.bit_buffer.ptr if va is not None else None, vout)
+    if rc:
+        check(rc, what)
+    return type(a)(data, dev, n, nb)
 
 
 def _unary(op: int, a: PrimitiveArrayGpu, out_cls=None, what="unary"):
-    dev = a.gpu_device
+    _ready(a)
+    dev, n, va = a.gpu_device, a.len, a._null_buffer
     out_cls = out_cls or type(a)
-    nb = _new_validity(dev, a.len, a.null_buffer)
-    out = out_cls.empty(a.len, dev, nb)
-    check(lib().agpu_unary(dev.handle, op, a.DTYPE, a.data.ptr, out.data.ptr, a.len,
-                           _vptr(a.null_buffer), _vptr(nb)), what)
-    return out
+    nb, vout = _alloc_validity(dev, n, va)
+    data = dev.create_empty_buffer(n * out_cls.ITEMSIZE)
+    rc = (_ffi._lib or lib()).agpu_unary(dev.handle, op, a.DTYPE, a._data.ptr, data.ptr, n,
+                                          va.bit_buffer.ptr if va is not None else None, vout)
+    if rc:
+        check(rc, what)
+    return out_cls(data, dev, n, nb)
 
 
 def _compare(op: int, a: PrimitiveArrayGpu, b: PrimitiveArrayGpu, what="compare") -> BooleanArrayGPU:
-    _check_same_len(a, b, what)
-    dev = a.gpu_device
-    nb = _new_validity(dev, a.len, a.null_buffer, b.null_buffer)
-    out = BooleanArrayGPU.empty(a.len, dev, nb)
-    check(lib().agpu_compare(dev.handle, op, a.DTYPE, a.data.ptr, b.data.ptr, out.data.ptr, a.len,
-                             _vptr(a.null_buffer), _vptr(b.null_buffer), _vptr(nb)), what)
-    return out
+    n = a.len
+    if n != b.len:
+        raise Panic(f"{what}: length mismatch {n} vs {b.len}")
+    _ready(a), _ready(b)
+    dev, va, vb = a.gpu_device, a._null_buffer, b._null_buffer
+    nb, vout = _alloc_validity(dev, n, va, vb)
+    data = dev.create_empty_buffer(((n + 31) >> 5) * 4)
+    rc = (_ffi._lib or lib()).agpu_compare(dev.handle, op, a.DTYPE, a._data.ptr, b._data.ptr, data.ptr, n,
+                                            va.bit_buffer.ptr if va is not None else None,
+                                            vb.bit_buffer.ptr if vb is not None else None, vout)
+    if rc:
+        check(rc, what)
+    return BooleanArrayGPU(data, dev, n, nb)
 
 
 def _shift(op: int, a: PrimitiveArrayGpu, counts: UInt32ArrayGPU, what="shift"):
-    _check_same_len(a, counts, what)
-    dev = a.gpu_device
-    nb = _new_validity(dev, a.len, a.null_buffer, counts.null_buffer)
-    out = type(a).empty(a.len, dev, nb)
-    check(lib().agpu_shift(dev.handle, op, a.DTYPE, a.data.ptr, counts.data.ptr, out.data.ptr, a.len,
-                           _vptr(a.null_buffer), _vptr(counts.null_buffer), _vptr(nb)), what)
-    return out
+    n = a.len
+    if n != counts.len:
+        raise Panic(f"{what}: length mismatch {n} vs {counts.len}")
+    _ready(a), _ready(counts)
+    dev, va, vb = a.gpu_device, a._null_buffer, counts._null_buffer
+    nb, vout = _alloc_validity(dev, n, va, vb)
+    data = dev.create_empty_buffer(n * a.ITEMSIZE)
+    rc = (_ffi._lib or lib()).agpu_shift(dev.handle, op, a.DTYPE, a._data.ptr, counts._data.ptr, data.ptr, n,
+                                          va.bit_buffer.ptr if va is not None else None,
+                                          vb.bit_buffer.ptr if vb is not None else None, vout)
+    if rc:
+        check(rc, what)
+    return type(a)(data, dev, n, nb)
 
 
 # ==========================================================================================
