@@ -11,3 +11,4 @@ from .array import GPU_DEVICE, ARRAY_BY_NAME, ARRAY_TYPES  # noqa: F401
 from .kernels import *  # noqa: F401,F403
 from . import kernels  # noqa: F401
 from .interop import from_arrow, to_arrow  # noqa: F401,E402
+from .c_device import export_device, from_arrow_device  # noqa: F401,E402

@@ -60,6 +60,7 @@ class GpuDevice {  // gpu_utils/gpu_device.rs:29-33
   GpuDevice& operator=(const GpuDevice&) = delete;
   agpu_device* handle() const { return h_; }
   void sync() const { check(agpu_sync(h_), "sync"); }
+  int ordinal() const { return agpu_device_ordinal(h_); }
   uint64_t launch_count() const { return agpu_launch_count(h_); }
  private:
   agpu_device* h_ = nullptr;
@@ -71,13 +72,17 @@ class ArrowGpuBuffer {  // array/buffer.rs:5-7 — owns one stream-ordered alloc
   ArrowGpuBuffer(DevicePtr dev, size_t bytes) : dev_(std::move(dev)), size_(bytes) {
     check(agpu_alloc(dev_->handle(), bytes ? bytes : 16, &ptr_), "create_empty_buffer");
   }
-  ~ArrowGpuBuffer() { if (ptr_) agpu_free(dev_->handle(), ptr_); }
+  // device memory owned by someone else (an imported ArrowDeviceArray): `owner` is dropped with the
+  // buffer, nothing is freed here
+  ArrowGpuBuffer(DevicePtr dev, void* foreign, size_t bytes, std::shared_ptr<void> owner)
+      : dev_(std::move(dev)), ptr_(foreign), size_(bytes), owner_(std::move(owner)), foreign_(true) {}
+  ~ArrowGpuBuffer() { if (ptr_ && !foreign_) agpu_free(dev_->handle(), ptr_); }
   ArrowGpuBuffer(const ArrowGpuBuffer&) = delete;
   void* ptr() const { return ptr_; }
   // the pointer, for work about to be enqueued on ANOTHER handle of the same GPU: the allocator
   // then keeps the block out of circulation after Drop until that handle's stream got there
   void* ptr_on(const DevicePtr& user) const {
-    if (user.get() != dev_.get()) check(agpu_buffer_record_use(user->handle(), ptr_), "record_use");
+    if (user.get() != dev_.get() && !foreign_) check(agpu_buffer_record_use(user->handle(), ptr_), "record_use");
     return ptr_;
   }
   uint64_t size() const { return size_; }
@@ -102,6 +107,8 @@ class ArrowGpuBuffer {  // array/buffer.rs:5-7 — owns one stream-ordered alloc
   DevicePtr dev_;
   void* ptr_ = nullptr;
   size_t size_;
+  std::shared_ptr<void> owner_;
+  bool foreign_ = false;
 };
 using BufferPtr = std::shared_ptr<ArrowGpuBuffer>;
 

@@ -32,3 +32,21 @@ extern "C" int agpu_cdata_apply(const char* op, const ArrowSchema* sa, const Arr
     return -2;
   }
 }
+
+// The same through the Arrow C Device Data Interface, zero-copy in both directions:
+// `in` (CUDA memory of device 0, e.g. exported by arrow_gpu_b200/c_device.py) is MOVED into the
+// mirror, out = op(in [, in]) stays on the device and is handed back as an ArrowDeviceArray.
+extern "C" int agpu_cdata_device_apply(const char* op, const ArrowSchema* schema, ArrowDeviceArray* in, ArrowSchema* out_schema,
+                                       ArrowDeviceArray* out) {
+  try {
+    static DevicePtr dev = std::make_shared<GpuDevice>(0);
+    ArrowArrayGPU a = import_arrow_device(schema, in, dev);
+    const std::string o(op);
+    if (o == "identity") { export_arrow_device(a, out_schema, out); return 0; }
+    if (o == "add") { export_arrow_device(add_dyn(a, a), out_schema, out); return 0; }
+    if (o == "gt") { export_arrow_device(gt_dyn(add_dyn(a, a), a), out_schema, out); return 0; }
+    return -1;
+  } catch (const std::exception&) {
+    return -2;
+  }
+}

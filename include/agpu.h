@@ -103,7 +103,9 @@ typedef enum { AGPU_SHL = 0, AGPU_SHR = 1 } agpu_shiftop;
 #define AGPU_ETIMEOUT (-5)     /* a peer GPU did not post its value (agpu_exchange_wait) */
 
 typedef struct agpu_device agpu_device; /* opaque: {ordinal, cudaStream_t, cudaMemPool_t} */
-typedef struct agpu_event agpu_event;   /* opaque cudaEvent_t wrapper */
+typedef struct agpu_event agpu_event;   /* cudaEvent_t wrapper; its first member IS the cudaEvent_t, so an agpu_event* can be
+                                           used as the `cudaEvent_t* sync_event` of an Arrow C Device Data Interface
+                                           ArrowDeviceArray, and such a sync_event can be passed to agpu_stream_wait_event */
 typedef struct agpu_graph agpu_graph;   /* opaque: a captured pipeline (cudaGraphExec_t + its temporaries) */
 
 /* ---- device / buffer layer: replaces GpuDevice (crates/array/src/gpu_utils/gpu_device.rs) ---- */
