@@ -124,13 +124,17 @@ int run_sum(agpu_device* dev, const T* a, size_t n, T* out_dev) {
 }
 
 // ---- any / all: logical/compute_shaders/u32/any.wgsl, countbitones.wgsl + Sum ----
-// mode 0 (any): flag when a word has a set bit; mode 1 (all): flag when a word has a clear bit
-// among the first n_bits.  `all` is finished by flipping the flag.
+// mode 0 (any): a word with a set bit; mode 1 (all): a word with a clear bit among the first n_bits.
+// One launch: warps that found something raise `found_flag` (word 1 of the handle's ticket block,
+// zero between launches), every CTA then takes a ticket and the last one writes the result and
+// puts both words back to zero — no memset before and no finishing kernel after (these ops are a
+// 5 us pass over a bitmap followed by a read-back: launches and the host round trip are the cost).
 __global__ void __launch_bounds__(kBlock) bits_find_kernel(const uint32_t* __restrict__ bits, const size_t nwords,
                                                            const size_t n_bits, const int mode, const int vec,
-                                                           uint32_t* __restrict__ flag) {
+                                                           unsigned int* __restrict__ ticket, uint32_t* __restrict__ result) {
   const uint32_t tail_mask = (n_bits & 31) ? ((1u << (n_bits & 31)) - 1u) : 0xFFFFFFFFu;
   const uint32_t flip = mode == 0 ? 0u : 0xFFFFFFFFu;  // all: look for a clear bit
+  unsigned int* found_flag = ticket + 1;
   uint32_t found = 0;
   // body: whole 16-byte chunks except the one holding the last word, 4 chunks in flight per thread
   const size_t nvec = vec ? (nwords - 1) / 4 : 0;
@@ -154,11 +158,17 @@ __global__ void __launch_bounds__(kBlock) bits_find_kernel(const uint32_t* __res
     if (w == nwords - 1) x &= tail_mask;
     found |= x;
   }
-  found = __reduce_or_sync(0xFFFFFFFFu, found);
-  if ((threadIdx.x & 31) == 0 && found) atomicOr(flag, 1u);
+  if (__syncthreads_or(found != 0) && threadIdx.x == 0) atomicOr(found_flag, 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();                                        // the flag is visible before the ticket
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {           // last CTA: every flag raised before its ticket is visible
+      __threadfence();
+      const unsigned int f = atomicExch(found_flag, 0u);
+      *result = mode == 0 ? (f ? 1u : 0u) : (f ? 0u : 1u);
+      *ticket = 0u;
+    }
+  }
 }
-
-__global__ void flip_flag_kernel(uint32_t* flag) { *flag = *flag ? 0u : 1u; }
 
 }  // namespace
 
@@ -187,17 +197,14 @@ extern "C" int agpu_sum(agpu_device* dev, int dtype, const void* a, size_t n, vo
 static int find_bits(agpu_device* dev, const uint32_t* bits, size_t n_bits, int mode, uint32_t* result_dev) {
   if (!dev) return AGPU_ENODEVICE;
   if (!result_dev || (n_bits && !bits)) return AGPU_EINVAL;
-  AGPU_CUDA(cudaMemsetAsync(result_dev, 0, 4, dev->stream));
+  if (!dev->ticket) return AGPU_ENODEVICE;
   const size_t nwords = (n_bits + 31) / 32;
-  if (nwords) {
-    size_t grid = ceil_div(nwords, (size_t)kBlock * 16);
-    const size_t cap = (size_t)dev->sm_count * 32;
-    if (grid > cap) grid = cap;
-    if (grid == 0) grid = 1;
-    AGPU_LAUNCH(dev, bits_find_kernel, (unsigned)grid, kBlock, 0, bits, nwords, n_bits, mode, aligned16(bits) ? 1 : 0,
-                result_dev);
-  }
-  if (mode == 1) AGPU_LAUNCH(dev, flip_flag_kernel, 1, 1, 0, result_dev);
+  size_t grid = ceil_div(nwords, (size_t)kBlock * 16);
+  const size_t cap = (size_t)dev->sm_count * 32;
+  if (grid > cap) grid = cap;
+  if (grid == 0) grid = 1;  // n_bits == 0: one CTA that finds nothing -> any = 0, all = 1
+  AGPU_LAUNCH(dev, bits_find_kernel, (unsigned)grid, kBlock, 0, bits, nwords, n_bits, mode,
+              nwords && aligned16(bits) ? 1 : 0, dev->ticket, result_dev);
   return agpu_finish_launch();
 }
 
