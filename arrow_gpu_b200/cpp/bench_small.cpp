@@ -20,6 +20,51 @@ using namespace arrow_gpu;
 int main(int argc, char** argv) {
   const bool json = argc > 1 && std::string(argv[1]) == "--json";   // one JSON object for bench.py's per_config.cfg1
   auto device = std::make_shared<GpuDevice>(0);
+  if (argc > 1 && std::string(argv[1]) == "--launch-floor") {
+    // what one op costs when the column is tiny (1 Ki rows): the host + driver floor under every
+    // per-op time above.  (a) the mirror's eager add/gt (2 allocations + launch + 2 frees),
+    // (b) the bare agpu_binary call into preallocated buffers, (c) allocation + free alone.
+    std::vector<std::optional<float>> a(1024, 1.0f);
+    a[3] = std::nullopt;
+    auto ga = Float32ArrayGPU::from_optional_slice(a, device);
+    auto gb = Float32ArrayGPU::from_optional_slice(a, device);
+    const int reps = 20000;
+    for (int i = 0; i < 1000; ++i) { auto s = ga.add(gb); }
+    device->sync();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; ++i) { auto s = ga.add(gb); auto g = ga.gt(gb); }
+    auto t1 = std::chrono::steady_clock::now();   // enqueue only: the host cost
+    device->sync();
+    auto t2 = std::chrono::steady_clock::now();
+    const double enq = std::chrono::duration<double, std::micro>(t1 - t0).count() / (2.0 * reps);
+    const double all = std::chrono::duration<double, std::micro>(t2 - t0).count() / (2.0 * reps);
+    auto out = ga.add(gb);
+    device->sync();
+    t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < 2 * reps; ++i)
+      agpu_binary(device->handle(), AGPU_ADD, AGPU_F32, ga.data->ptr(), gb.data->ptr(), out.data->ptr(), 1024,
+                  (const uint32_t*)ga.null_buffer->bit_buffer->ptr(), (const uint32_t*)gb.null_buffer->bit_buffer->ptr(),
+                  (uint32_t*)out.null_buffer->bit_buffer->ptr());
+    t1 = std::chrono::steady_clock::now();
+    device->sync();
+    t2 = std::chrono::steady_clock::now();
+    const double bare_enq = std::chrono::duration<double, std::micro>(t1 - t0).count() / (2.0 * reps);
+    const double bare_all = std::chrono::duration<double, std::micro>(t2 - t0).count() / (2.0 * reps);
+    t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < 2 * reps; ++i) {
+      void* p = nullptr;
+      void* q = nullptr;
+      agpu_alloc(device->handle(), 4096, &p);
+      agpu_alloc(device->handle(), 128, &q);
+      agpu_free(device->handle(), p);
+      agpu_free(device->handle(), q);
+    }
+    t1 = std::chrono::steady_clock::now();
+    const double alloc2 = std::chrono::duration<double, std::micro>(t1 - t0).count() / (2.0 * reps);
+    std::printf("launch floor, 1 Ki-row f32 columns with validity, us per op: mirror eager %.2f enqueue / %.2f incl. drain; "
+                "bare agpu_binary %.2f enqueue / %.2f incl. drain; 2 x (alloc + free) %.2f\n", enq, all, bare_enq, bare_all, alloc2);
+    return 0;
+  }
   if (json) std::printf("{\"what\": \"C++ host mirror (arrow_gpu.hpp), f32 add + gt with null bitmaps, cold inputs (rotating copies >= 512 MiB), "
                         "wall clock over >= 512 submissions; frac = algorithmic GB/s / 6541.1\", \"sizes\": {");
   bool first_size = true;
