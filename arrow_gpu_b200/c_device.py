@@ -197,17 +197,19 @@ class _Imported:
         self.ptr, self.device = moved_ptr, device
 
     def __del__(self):
-        try:
-            if self.ptr:
-                d = C.cast(self.ptr, C.POINTER(ArrowDeviceArray)).contents
-                if d.array.release:
-                    if self.device.handle:
-                        self.device.sync()      # kernels of this handle may still read the producer's memory
-                    d.array.release(C.pointer(d.array))
-                _libc.free(self.ptr)
-        except Exception:
-            pass
-        self.ptr = None
+        ptr, self.ptr = self.ptr, None
+        if not ptr:
+            return
+        d = C.cast(ptr, C.POINTER(ArrowDeviceArray)).contents
+        if d.array.release:
+            try:
+                if self.device.handle:
+                    self.device.sync()          # kernels of this handle may still read the producer's memory
+            except Exception as exc:            # a failed wait must not leak the producer's buffers
+                import warnings
+                warnings.warn(f"arrow_gpu_b200: sync before releasing an imported ArrowDeviceArray failed: {exc}")
+            d.array.release(C.pointer(d.array))
+        _libc.free(ptr)
 
 
 class _ForeignBuffer(ArrowGpuBuffer):
