@@ -332,7 +332,8 @@ def link_ceiling_probe(dev, up, down, lib, ffi, sharded, h2d_bytes, d2h_bytes, s
     """What the host <-> device links give ALL ranks at once with plain cudaMemcpyAsync from/to pinned
     memory and nothing else running: the e2e step's own byte counts in both directions, H2D and
     D2H concurrently on two streams.  e2e cannot beat this; `link_frac` says how close it gets."""
-    chunk = min(len(src_pinned), len(dst_pinned), dev_buf.size)
+    dst_list = dst_pinned if isinstance(dst_pinned, (list, tuple)) else [dst_pinned]   # the e2e step alternates landing buffers
+    chunk = min(len(src_pinned), min(len(d) for d in dst_list), dev_buf.size)
 
     def once():
         sent = 0
@@ -340,11 +341,12 @@ def link_ceiling_probe(dev, up, down, lib, ffi, sharded, h2d_bytes, d2h_bytes, s
             n = min(chunk, h2d_bytes - sent)
             ffi.check(lib.agpu_h2d(up.handle, dev_buf.ptr, src_pinned.ctypes.data, n), "h2d")
             sent += n
-        got = 0
+        got, k = 0, 0
         while got < d2h_bytes:
             n = min(chunk, d2h_bytes - got)
-            ffi.check(lib.agpu_d2h_async(down.handle, dst_pinned.ctypes.data, dev_buf.ptr, n), "d2h")
+            ffi.check(lib.agpu_d2h_async(down.handle, dst_list[k % len(dst_list)].ctypes.data, dev_buf.ptr, n), "d2h")
             got += n
+            k += 1
         up.sync()
         down.sync()
 
@@ -488,13 +490,17 @@ def run_ours(args, rank, world, local_rank, sampler, numa):
         sharded.barrier()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         t0 = time.perf_counter()
+        each = []
         for _ in range(e2e_steps):
+            t1 = time.perf_counter()
             h2d, d2h = e2e_step()
+            each.append(round((time.perf_counter() - t1) * 1e3, 1))
         e2e_ms = sharded.max_over_ranks((time.perf_counter() - t0) * 1e3)
         step_ms = e2e_ms / e2e_steps
         e2e = {"value": len(ops) * rows * e2e_steps * world / (e2e_ms * 1e-3), "unit": "rows/s", "steps": e2e_steps,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(step_ms, 3),
                "pcie_GBps": {"h2d": round(h2d / (step_ms * 1e-3) / 1e9, 1), "d2h": round(d2h / (step_ms * 1e-3) / 1e9, 1)},
+               "ms_each_step_rank0": each,
                "streams": "upload / compute / download on three handles, two landing buffers"}
         # where the e2e time goes: the same step with the 55 result columns left on the device
         t0 = time.perf_counter()
@@ -503,7 +509,7 @@ def run_ours(args, rank, world, local_rank, sampler, numa):
         # and what the links give all ranks at once for these byte counts with nothing else going on
         scratch = dev.create_empty_buffer(rows * 4)
         probe_ms = link_ceiling_probe(dev, up, down, lib, _ffi, sharded, h2d, d2h, pinned["cnt8"].view(np.uint8),
-                                      landing[0], scratch)
+                                      landing, scratch)
         del scratch
         e2e["link_probe_ms_per_step"] = round(probe_ms, 3)
         e2e["link_GBps_ceiling"] = {"h2d": round(h2d / (probe_ms * 1e-3) / 1e9, 1), "d2h": round(d2h / (probe_ms * 1e-3) / 1e9, 1),
@@ -667,7 +673,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=None,
                     help="rows of the CPU sample (default: the full columns — a step is 1-4 s of CPU work on 16-32 host "
                          "threads, and a sample that fits the host's last-level cache would flatter the CPU)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
