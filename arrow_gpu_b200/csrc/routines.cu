@@ -528,7 +528,15 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
     if (gstart + 32 + lane < t0) before += counts[gstart + 32 + lane];
     if (lane == 0) goff = group_offsets[t0 / kFilterGroupTiles];
   }
-  for (int w = threadIdx.x; w < WORDS; w += BLOCK) sel[w] = sel_word(mask, vmask, w0 + w, nwords, n);
+  if (full) {  // no ragged word in this tile: plain loads
+    for (int w = threadIdx.x; w < WORDS; w += BLOCK) {
+      uint32_t x = mask[w0 + w];
+      if (vmask) x &= vmask[w0 + w];
+      sel[w] = x;
+    }
+  } else {
+    for (int w = threadIdx.x; w < WORDS; w += BLOCK) sel[w] = sel_word(mask, vmask, w0 + w, nwords, n);
+  }
   if (warp == 1) {
 #pragma unroll
     for (int off = 16; off; off >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, off);
@@ -579,6 +587,8 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(U) == 1 ? 1536 : 2048) / BLOCK)
       if constexpr (sizeof(U) < 4) {
         uint32_t w[4];
         memcpy(w, &v[j], 16);
+        // (two independent address chains per granule instead of one serial chain of predicated
+        // bumps: measured, no difference — 162.6 vs 164.2 us for 1-byte rows)
         stage_lanes<U, 0>(sa, w, bits);
         if (HAS_V) {
 #pragma unroll
