@@ -489,19 +489,27 @@ def run_ours(args, rank, world, local_rank, sampler, numa):
         e2e_step()
         sharded.barrier()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        t0 = time.perf_counter()
-        each = []
-        for _ in range(e2e_steps):
-            t1 = time.perf_counter()
-            h2d, d2h = e2e_step()
-            each.append(round((time.perf_counter() - t1) * 1e3, 1))
-        e2e_ms = sharded.max_over_ranks((time.perf_counter() - t0) * 1e3)
-        step_ms = e2e_ms / e2e_steps
-        e2e = {"value": len(ops) * rows * e2e_steps * world / (e2e_ms * 1e-3), "unit": "rows/s", "steps": e2e_steps,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(step_ms, 3),
-               "pcie_GBps": {"h2d": round(h2d / (step_ms * 1e-3) / 1e9, 1), "d2h": round(d2h / (step_ms * 1e-3) / 1e9, 1)},
-               "ms_each_step_rank0": each,
-               "streams": "upload / compute / download on three handles, two landing buffers"}
+
+        def timed_e2e():
+            t0 = time.perf_counter()
+            each = []
+            for _ in range(e2e_steps):
+                t1 = time.perf_counter()
+                moved = e2e_step()
+                each.append(round((time.perf_counter() - t1) * 1e3, 1))
+            return sharded.max_over_ranks((time.perf_counter() - t0) * 1e3), each, moved
+
+        def e2e_block(e2e_ms, each, moved):
+            h2d, d2h = moved
+            step_ms = e2e_ms / e2e_steps
+            return {"value": len(ops) * rows * e2e_steps * world / (e2e_ms * 1e-3), "unit": "rows/s", "steps": e2e_steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(step_ms, 3),
+                    "pcie_GBps": {"h2d": round(h2d / (step_ms * 1e-3) / 1e9, 1), "d2h": round(d2h / (step_ms * 1e-3) / 1e9, 1)},
+                    "ms_each_step_rank0": each,
+                    "streams": "upload / compute / download on three handles, two landing buffers"}
+
+        e2e = e2e_block(*timed_e2e())
+        h2d, d2h = e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"]
         # where the e2e time goes: the same step with the 55 result columns left on the device
         t0 = time.perf_counter()
         e2e_step(read_back=False)
@@ -515,7 +523,20 @@ def run_ours(args, rank, world, local_rank, sampler, numa):
         e2e["link_GBps_ceiling"] = {"h2d": round(h2d / (probe_ms * 1e-3) / 1e9, 1), "d2h": round(d2h / (probe_ms * 1e-3) / 1e9, 1),
                                     "how": "plain cudaMemcpyAsync, pinned, H2D and D2H concurrently, all ranks at once, "
                                            "the e2e step's byte counts"}
-        e2e["link_frac"] = round(probe_ms / step_ms, 4)
+        e2e["link_frac"] = round(probe_ms / e2e["ms_per_step"], 4)
+        # The host links are shared with whatever else runs on the box.  A measurement far below what
+        # the same links gave seconds later (plain copies of the same bytes) saw an outside
+        # disturbance: like a run with a thermal slowdown it is rejected and re-measured ONCE; the
+        # rejected attempt stays in the line.
+        if e2e["link_frac"] < args.e2e_remeasure_below:
+            first = {k: e2e[k] for k in ("value", "ms_per_step", "ms_each_step_rank0", "link_frac")}
+            again = e2e_block(*timed_e2e())
+            again["link_frac"] = round(probe_ms / again["ms_per_step"], 4)
+            for k in ("upload_and_compute_only_ms_per_step", "link_probe_ms_per_step", "link_GBps_ceiling"):
+                again[k] = e2e[k]
+            again["remeasured_once"] = {"why": f"first attempt ran at < {args.e2e_remeasure_below} of the link ceiling measured right after it",
+                                        "rejected_attempt": first}
+            e2e = again
 
     # ---- full-size parity: each of the 55 outputs vs the oracle on the same host columns ----
     parity = None
@@ -674,6 +695,8 @@ def main():
                     help="rows of the CPU sample (default: the full columns — a step is 1-4 s of CPU work on 16-32 host "
                          "threads, and a sample that fits the host's last-level cache would flatter the CPU)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-remeasure-below", type=float, default=0.6,
+                    help="re-measure e2e once when it ran below this fraction of the link ceiling (outside disturbance)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
