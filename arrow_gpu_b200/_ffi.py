@@ -98,8 +98,10 @@ class ChainStep(C.Structure):
 STEP_UNARY, STEP_BINARY_COLUMN, STEP_BINARY_SCALAR, STEP_COMPARE_COLUMN, STEP_COMPARE_SCALAR = range(5)
 STEP_BINARY_DEVSCALAR, STEP_COMPARE_DEVSCALAR = 5, 6
 STEP_SHIFT_COLUMN = 7
+STEP_STORE, STEP_RESET = 8, 9          # agpu_fused_chain_pair only
 CHAIN_MAX_STEPS = 8
 SIGNATURES["agpu_fused_chain"] = (_i, [_p, _i, _p, _u32p, C.POINTER(ChainStep), _i, _p, _sz, _u32p])
+SIGNATURES["agpu_fused_chain_pair"] = (_i, [_p, _i, _p, _u32p, C.POINTER(ChainStep), _i, _p, _p, _sz, _u32p])
 SIGNATURES["agpu_fused_chain_int"] = (_i, [_p, _i, _p, _u32p, C.POINTER(ChainStep), _i, _p, _sz, _u32p])
 
 _lib = None

@@ -760,6 +760,41 @@ class DeviceScalar:
         self.array = array
 
 
+def _encode_chain_steps(data, steps, arr, at, validities, what="fused_chain"):
+    """fills arr[at : at + len(steps)] with the agpu_chain_step form of `steps`; appends the operand
+    columns' validity buffers to `validities`; returns True when the last step is a compare"""
+    is_pred = False
+    for k, step in enumerate(steps):
+        name, operand = step[0], (step[1] if len(step) > 1 else None)
+        slot = arr[at + k]
+        if name in _CHAIN_UNARY and operand is None:
+            slot.kind, slot.op = _ffi.STEP_UNARY, _CHAIN_UNARY[name]
+            continue
+        if name in _CHAIN_BINARY:
+            op, kinds = _CHAIN_BINARY[name], (_ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_SCALAR, _ffi.STEP_BINARY_DEVSCALAR)
+        elif name in _CHAIN_COMPARE:
+            if k != len(steps) - 1:
+                raise Panic("a compare can only end a fused chain")
+            op, kinds, is_pred = (_CHAIN_COMPARE[name],
+                                  (_ffi.STEP_COMPARE_COLUMN, _ffi.STEP_COMPARE_SCALAR, _ffi.STEP_COMPARE_DEVSCALAR), True)
+        else:
+            raise Panic(f"{what}: unknown step {step!r}")
+        slot.op = op
+        if isinstance(operand, DeviceScalar):
+            if not isinstance(operand.array, Float32ArrayGPU):
+                raise Panic(f"{what}: a device scalar must be a one-element Float32ArrayGPU")
+            slot.kind, slot.operand = kinds[2], operand.array.data.ptr
+        elif isinstance(operand, Float32ArrayGPU):
+            _check_same_len(data, operand, what)
+            slot.kind, slot.operand, slot.validity = kinds[0], operand.data.ptr, _vptr(operand.null_buffer)
+            validities.append(operand.null_buffer)
+        elif isinstance(operand, (int, float, np.floating, np.integer)):
+            slot.kind, slot.scalar = kinds[1], float(operand)
+        else:
+            raise Panic(f"{what}: operand of {name!r} must be a Float32ArrayGPU or a number")
+    return is_pred
+
+
 def fused_chain_op(data, steps, pipeline):
     """Evaluate a linear chain in ONE kernel.  `steps` is a list of
          ("sqrt",)                 unary f32 op on the running value
@@ -774,40 +809,83 @@ def fused_chain_op(data, steps, pipeline):
         raise Panic(f"fused_chain takes 1..{_ffi.CHAIN_MAX_STEPS} steps")
     arr = (_ffi.ChainStep * len(steps))()
     validities = [data.null_buffer]
-    is_pred = False
-    for k, step in enumerate(steps):
-        name, operand = step[0], (step[1] if len(step) > 1 else None)
-        if name in _CHAIN_UNARY and operand is None:
-            arr[k].kind, arr[k].op = _ffi.STEP_UNARY, _CHAIN_UNARY[name]
-            continue
-        if name in _CHAIN_BINARY:
-            op, kinds = _CHAIN_BINARY[name], (_ffi.STEP_BINARY_COLUMN, _ffi.STEP_BINARY_SCALAR, _ffi.STEP_BINARY_DEVSCALAR)
-        elif name in _CHAIN_COMPARE:
-            if k != len(steps) - 1:
-                raise Panic("a compare can only end a fused chain")
-            op, kinds, is_pred = (_CHAIN_COMPARE[name],
-                                  (_ffi.STEP_COMPARE_COLUMN, _ffi.STEP_COMPARE_SCALAR, _ffi.STEP_COMPARE_DEVSCALAR), True)
-        else:
-            raise Panic(f"fused_chain: unknown step {step!r}")
-        arr[k].op = op
-        if isinstance(operand, DeviceScalar):
-            if not isinstance(operand.array, Float32ArrayGPU):
-                raise Panic("fused_chain: a device scalar must be a one-element Float32ArrayGPU")
-            arr[k].kind, arr[k].operand = kinds[2], operand.array.data.ptr
-        elif isinstance(operand, Float32ArrayGPU):
-            _check_same_len(data, operand, "fused_chain")
-            arr[k].kind, arr[k].operand, arr[k].validity = kinds[0], operand.data.ptr, _vptr(operand.null_buffer)
-            validities.append(operand.null_buffer)
-        elif isinstance(operand, (int, float, np.floating, np.integer)):
-            arr[k].kind, arr[k].scalar = kinds[1], float(operand)
-        else:
-            raise Panic(f"fused_chain: operand of {name!r} must be a Float32ArrayGPU or a number")
+    is_pred = _encode_chain_steps(data, steps, arr, 0, validities)
     dev = data.gpu_device
     _note_foreign_buffers(dev, [data] + [st[1] for st in steps if len(st) > 1 and isinstance(st[1], PrimitiveArrayGpu)])
     nb = _new_validity(dev, data.len, *validities)
     out = (BooleanArrayGPU if is_pred else Float32ArrayGPU).empty(data.len, dev, nb)
     check(lib().agpu_fused_chain(dev.handle, data.DTYPE, data.data.ptr, _vptr(data.null_buffer), arr, len(steps),
                                  out.data.ptr, data.len, _vptr(nb)), "fused_chain")
+    return out
+
+
+# ---- two results of one source column in one pass (agpu_fused_chain_pair) ----
+_PAIR_STEPS = {"neg", "abs", "sqrt", "add", "sub", "mul", "div", "rem", "min", "max"} | set(_CHAIN_COMPARE)
+
+
+def _step_columns(steps):
+    return [st[1] for st in steps if len(st) > 1 and isinstance(st[1], PrimitiveArrayGpu)]
+
+
+def _validity_set(data, steps):
+    """the device bitmaps a chain's validity is the AND of (by address)"""
+    return {nb.bit_buffer.ptr for nb in [data.null_buffer] + [c.null_buffer for c in _step_columns(steps)] if nb is not None}
+
+
+def pair_eligible(data, value_steps, pred_steps) -> bool:
+    """can `value_steps` and `pred_steps` (both starting at `data`) run as ONE agpu_fused_chain_pair
+    kernel with results identical to the two chains run separately?"""
+    if not isinstance(data, Float32ArrayGPU) or not value_steps or not pred_steps:
+        return False
+    if len(value_steps) + len(pred_steps) + 2 > _ffi.CHAIN_MAX_STEPS:
+        return False
+    if any(st[0] not in _PAIR_STEPS for st in value_steps + pred_steps):
+        return False
+    if any(st[0] in _CHAIN_COMPARE for st in value_steps) or pred_steps[-1][0] not in _CHAIN_COMPARE:
+        return False
+    if any(st[0] in _CHAIN_COMPARE for st in pred_steps[:-1]):
+        return False
+    cols = _step_columns(value_steps + pred_steps)
+    if any(not isinstance(c, Float32ArrayGPU) or c.len != data.len for c in cols):
+        return False
+    if len({c.data.ptr for c in cols}) > _MAX_CHAIN_COLS:
+        return False
+    # the kernel writes ONE validity bitmap (AND of every input's): right for both results only
+    # when both chains depend on the same bitmaps
+    return _validity_set(data, value_steps) == _validity_set(data, pred_steps)
+
+
+def fused_chain_pair_op(data, value_steps, pred_steps, pipeline):
+    """`fused_chain_op(data, value_steps)` and `fused_chain_op(data, pred_steps)` in ONE kernel: the
+    source and every operand column are read once, e.g. the first benchmark program of the
+    reference, s = a + b; g = a > b:  fused_chain_pair(a, [("add", b)], [("gt", b)]) -> (s, g).
+    f32 columns, arithmetic steps (neg abs sqrt + - * / % min max) and a closing compare in the
+    second chain; both chains must depend on the same validity bitmaps (`pair_eligible`).  The two
+    results share one validity buffer (bitmaps are never modified in place)."""
+    if not pair_eligible(data, value_steps, pred_steps):
+        raise Panic("fused_chain_pair: the two chains cannot share one kernel (see pair_eligible)")
+    nv, npred = len(value_steps), len(pred_steps)
+    arr = (_ffi.ChainStep * (nv + npred + 2))()
+    validities = [data.null_buffer]
+    _encode_chain_steps(data, value_steps, arr, 0, validities, "fused_chain_pair")
+    arr[nv].kind, arr[nv + 1].kind = _ffi.STEP_STORE, _ffi.STEP_RESET
+    _encode_chain_steps(data, pred_steps, arr, nv + 2, validities, "fused_chain_pair")
+    dev = data.gpu_device
+    _note_foreign_buffers(dev, [data] + _step_columns(value_steps + pred_steps))
+    n = data.len
+    vbuf = dev.create_empty_buffer(bitmap_words(n) * 4) if any(v is not None for v in validities) else None
+    value = Float32ArrayGPU.empty(n, dev, NullBitBufferGpu(vbuf, n, dev) if vbuf is not None else None)
+    pred = BooleanArrayGPU.empty(n, dev, NullBitBufferGpu(vbuf, n, dev) if vbuf is not None else None)
+    check(lib().agpu_fused_chain_pair(dev.handle, data.DTYPE, data.data.ptr, _vptr(data.null_buffer), arr, len(arr),
+                                      value.data.ptr, pred.data.ptr, n, vbuf.ptr if vbuf is not None else None),
+          "fused_chain_pair")
+    return value, pred
+
+
+def fused_chain_pair(data, value_steps, pred_steps):
+    pipeline = _pipeline_for(data)
+    out = fused_chain_pair_op(data, value_steps, pred_steps, pipeline)
+    pipeline.finish()
     return out
 
 
@@ -1020,7 +1098,31 @@ def _try_fuse(name, self, args):
         return _lazy_array(*_extend(self, (base, operand), pipeline), pipeline)
     if base in _FUSE_COMPARE:
         source, steps = _extend(self, (base, operand), pipeline)
+        partner = _pending_value_chain(pipeline, source, steps)
+        if partner is not None:
+            # a recorded value chain over the same source is still waiting (s = a + b; g = a > b):
+            # both results come out of ONE kernel that reads the shared columns once
+            value, pred = fused_chain_pair_op(source, partner._lazy.steps, steps, pipeline)
+            partner._lazy = None
+            partner._data, partner._null_buffer = value._data, value._null_buffer
+            return pred
         return fused_chain_op(source, steps, pipeline)       # a predicate ends the chain: launch now
+    return None
+
+
+def _pending_value_chain(pipeline, source, pred_steps):
+    """the most recently recorded, not yet launched f32 value chain of `pipeline` that starts at the
+    same source column as the predicate chain about to be launched and may share its kernel"""
+    for ref in reversed(pipeline._lazies):
+        arr = ref()
+        lazy = arr._lazy if arr is not None else None
+        if (lazy is None or lazy.consumed or lazy.mode != "f32" or lazy.pipeline is not pipeline or lazy.source is not source
+                or any(c is arr for c in _step_columns(pred_steps))):      # the predicate reads this very result
+            continue
+        # looking at the operands launches the ones that are still recorded chains; if one of them
+        # depended on `arr`, that launched `arr` too and there is nothing left to pair with
+        if pair_eligible(source, lazy.steps, pred_steps) and arr._lazy is lazy:
+            return arr
     return None
 
 

@@ -556,10 +556,49 @@ def _cfg1_block(ctx, args, peak, handles, numa):
         dev.sync()
         b2b_eager_us = T.ms(e0, e1) / (rounds * len(pairs)) * 1e3
         del x, y
+        # the same program with both results out of ONE kernel (agpu_fused_chain_pair: a and b are read
+        # once, the validity AND is written once): what ArrowComputePipeline(fuse=True) records for
+        # add_op followed by gt_op; captured, it is a one-kernel graph
+        from arrow_gpu_b200 import kernels as K
+        fprogs = []
+        for a, b in pairs:
+            p = ag.ArrowComputePipeline(dev, "cfg1 fused", fuse=True, capture=True)
+            s = a.add_op(b, p)
+            g = a.gt_op(b, p)
+            p.finish()
+            fprogs.append((p, s, g))
+        dev.sync()
+        T.record(e0)
+        for _ in range(rounds):
+            for p, _s, _g in fprogs:
+                p.replay()
+        T.record(e1)
+        dev.sync()
+        b2b_fused_graph_us = T.ms(e0, e1) / (rounds * len(fprogs)) * 1e3
+        T.record(e0)
+        for _ in range(rounds):
+            for a, b in pairs:
+                x, y = K.fused_chain_pair(a, [("add", b)], [("gt", b)])
+        T.record(e1)
+        dev.sync()
+        b2b_fused_eager_us = T.ms(e0, e1) / (rounds * len(pairs)) * 1e3
+        del x, y
+        fused_bytes = 12.5 * n          # a, b once (8), sum (4), result bitmap, two validity reads + one write (4 x 0.125)
         for e0, e1 in ev:
             lib.agpu_event_destroy(e0)
             lib.agpu_event_destroy(e1)
         entry = {"input_copies": copies, "per_op_eager": per_op,
+                 "fused_pair": {"what": "add + gt as ONE kernel (agpu_fused_chain_pair): recorded on ArrowComputePipeline(fuse=True, "
+                                        "capture=True) and replayed / called eagerly as kernels.fused_chain_pair; back to back, cold "
+                                        "inputs; frac_of_unfused_bytes counts the 20.875 B/row the two separate ops move, "
+                                        "frac_measured_peak the 12.5 B/row this kernel moves",
+                                "kernels_per_submit": fprogs[0][0].graph.kernels,
+                                "captured_us_per_program": round(b2b_fused_graph_us, 2),
+                                "captured_frac_measured_peak": round(fused_bytes / (b2b_fused_graph_us * 1e-6) / 1e9 / peak, 4),
+                                "captured_frac_of_unfused_bytes": round(prog_bytes / (b2b_fused_graph_us * 1e-6) / 1e9 / peak, 4),
+                                "eager_us_per_program": round(b2b_fused_eager_us, 2),
+                                "eager_frac_measured_peak": round(fused_bytes / (b2b_fused_eager_us * 1e-6) / 1e9 / peak, 4),
+                                "eager_frac_of_unfused_bytes": round(prog_bytes / (b2b_fused_eager_us * 1e-6) / 1e9 / peak, 4)},
                  "captured_program": {"what": "add_op + gt_op recorded on ArrowComputePipeline(capture=True), one graph launch per iteration, "
                                               "one event pair per submit",
                                       "ms": round(prog_ms, 4), "GBps": round(prog_bytes / (prog_ms * 1e-3) / 1e9, 1),
@@ -578,12 +617,12 @@ def _cfg1_block(ctx, args, peak, handles, numa):
             want_g = O.compare(O.GT, O.F32, ex["a_h"], ex["b_h"])
             want_v = O.validity_and(O.pack_bits(ex["va"]), O.pack_bits(ex["vb"]), n)
             bad = 0
-            for got_s, got_g in ((a.add(b), a.gt(b)), (s, g)):
+            for got_s, got_g in ((a.add(b), a.gt(b)), (s, g), fprogs[0][1:], K.fused_chain_pair(a, [("add", b)], [("gt", b)])):
                 bad += int(np.count_nonzero(got_s.raw_values().view(np.uint32) != want_s.view(np.uint32)))
                 bad += int(np.count_nonzero(_d2h(ctx, got_g.data.ptr, O.words(n) * 4, np.uint32) != want_g))
                 for arr in (got_s, got_g):
                     bad += int(np.count_nonzero(_d2h(ctx, arr.null_buffer.bit_buffer.ptr, O.words(n) * 4, np.uint32) != want_v))
-            block["parity"] = {"ops": 2, "rows": n, "mismatches": bad, "how": "values, result bitmap and validity words, eager and captured, vs the oracle"}
+            block["parity"] = {"ops": 2, "rows": n, "mismatches": bad, "how": "values, result bitmap and validity words; eager, captured, fused pair (captured and eager) vs the oracle"}
             cpu_s = _time_cpu(lambda: (O.binary(O.ADD, O.F32, ex["a_h"], ex["b_h"]), O.compare(O.GT, O.F32, ex["a_h"], ex["b_h"]),
                                        O.validity_and(O.pack_bits(ex["va"]), O.pack_bits(ex["vb"]), n)), 0.3, 200)
             block["cpu_baseline"] = {"value": 2 * n / cpu_s, "unit": "rows/s", "cores": O.num_threads(), "kind": "port",
@@ -620,7 +659,7 @@ def _cfg1_block(ctx, args, peak, handles, numa):
                 dev.pinned_free(buf)
             del a, b
         block["sizes"][f"{n} rows"] = entry
-        del progs, pairs, ops, ex, p, s, g
+        del progs, fprogs, pairs, ops, ex, p, s, g
         import gc
         gc.collect()
     block["_window"] = (window0, time.time())

@@ -272,7 +272,10 @@ typedef enum {
   AGPU_STEP_COMPARE_DEVSCALAR = 6,
   /* agpu_fused_chain_int only: acc = acc << / >> counts[i]; op = AGPU_SHL / AGPU_SHR, operand = a
    * u32 column of per-row counts (logical/src/lib.rs:160-186), validity = its bitmap */
-  AGPU_STEP_SHIFT_COLUMN = 7
+  AGPU_STEP_SHIFT_COLUMN = 7,
+  /* agpu_fused_chain_pair only: out_value[i] = acc / acc = f32(in[i]) again */
+  AGPU_STEP_STORE = 8,
+  AGPU_STEP_RESET = 9
 } agpu_step_kind;
 typedef struct {
   int32_t kind;             /* agpu_step_kind */
@@ -284,6 +287,20 @@ typedef struct {
 } agpu_chain_step;
 int agpu_fused_chain(agpu_device* dev, int in_dtype, const void* in, const uint32_t* vin,
                      const agpu_chain_step* steps, int n_steps, void* out, size_t n, uint32_t* vout);
+
+/* TWO results of one source column in ONE pass: a value chain and a predicate chain, e.g. the
+ * reference's first benchmark program  s = a + b;  g = a > b  (BASELINE.json configs[0]) reads a
+ * and b once instead of twice and is one launch instead of two.  steps =
+ *   value-chain steps, AGPU_STEP_STORE, AGPU_STEP_RESET, predicate-chain steps (last one a compare)
+ * in_dtype F32 only; the steps are the arithmetic ones (NEG ABS SQRT, ADD SUB MUL DIV REM MIN MAX,
+ * compares), <= AGPU_CHAIN_MAX_STEPS including STORE and RESET, <= 3 DISTINCT operand columns (a
+ * column used by both chains counts once and is loaded once).  Every step rounds like the
+ * stand-alone kernel, so both results are bit-identical to the two chains run separately.  ONE
+ * validity bitmap is written: vout = AND of vin and of every operand column's bitmap — the caller
+ * pairs only chains whose validity inputs are the same set. */
+int agpu_fused_chain_pair(agpu_device* dev, int in_dtype, const void* in, const uint32_t* vin,
+                          const agpu_chain_step* steps, int n_steps, float* out_value, uint32_t* out_bits,
+                          size_t n, uint32_t* vout);
 
 /* The same chain machinery on INTEGER columns (dtype = I8 U8 I16 U16 I32 U32 DATE32): the running
  * value, every operand column and every device scalar have type `dtype`, and each step is the

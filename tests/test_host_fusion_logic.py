@@ -15,7 +15,7 @@ from arrow_gpu_b200 import kernels as K
 pytestmark = pytest.mark.timeout(120)
 
 LAUNCHING = ("agpu_binary", "agpu_scalar", "agpu_unary", "agpu_compare", "agpu_shift", "agpu_cast", "agpu_fused_chain",
-             "agpu_fused_chain_int", "agpu_fused_mul_add_gt", "agpu_bitmap_binary", "agpu_bitmap_not", "agpu_merge",
+             "agpu_fused_chain_int", "agpu_fused_chain_pair", "agpu_fused_mul_add_gt", "agpu_bitmap_binary", "agpu_bitmap_not", "agpu_merge",
              "agpu_take")
 
 
@@ -242,3 +242,112 @@ def test_captured_pipeline_brackets_the_ops_with_graph_begin_and_end(stub):
     names = [n for n, _a in lib.calls if n.startswith("agpu_graph") or n in LAUNCHING]
     assert names == ["agpu_graph_begin", "agpu_binary", "agpu_compare", "agpu_graph_end", "agpu_graph_kernel_count",
                      "agpu_graph_launch", "agpu_graph_launch"], names
+
+
+# ---- value chain + predicate chain over the same source: one agpu_fused_chain_pair launch ----
+def f32v(dev, n=64):
+    return ag.Float32ArrayGPU.from_numpy(np.ones(n, np.float32), np.arange(n) % 3 != 0, dev)
+
+
+def test_add_then_gt_on_the_same_columns_is_one_kernel(stub):
+    """BASELINE.json configs[0]: s = a + b; g = a > b"""
+    lib, dev = stub
+    for make in (f32, f32v):
+        a, b = make(dev), make(dev)
+        lib.calls.clear()
+        p = ag.ArrowComputePipeline(dev, fuse=True)
+        s = K.add_op_dyn(a, b, p)
+        assert lib.launched() == []
+        g = K.gt_op_dyn(a, b, p)
+        (name, steps), = lib.launched()
+        assert name == "agpu_fused_chain_pair"
+        assert [(k, o) for k, o, _p, _s in steps] == [(_ffi.STEP_BINARY_COLUMN, _ffi.ADD), (_ffi.STEP_STORE, 0), (_ffi.STEP_RESET, 0),
+                                                      (_ffi.STEP_COMPARE_COLUMN, _ffi.GT)]
+        assert steps[0][2] == b.data.ptr and steps[3][2] == b.data.ptr
+        assert s._lazy is None and s._data is not None and isinstance(g, ag.BooleanArrayGPU)
+        if make is f32v:
+            assert s.null_buffer.bit_buffer is g.null_buffer.bit_buffer        # one bitmap, written once
+        else:
+            assert s.null_buffer is None and g.null_buffer is None
+        p.finish()
+        assert len(lib.launched()) == 1                                         # nothing left to launch
+
+
+def test_pairing_needs_the_same_validity_inputs_and_arithmetic_steps(stub):
+    lib, dev = stub
+    a, b, c = f32(dev), f32(dev), f32v(dev)
+    # g depends on c's bitmap, s does not: two kernels
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    s = K.add_op_dyn(a, b, p)
+    K.gt_op_dyn(a, c, p)
+    p.finish()
+    assert sorted(n for n, _ in lib.launched()) == ["agpu_fused_chain", "agpu_fused_chain"]
+    # a transcendental in the value chain: the pair kernel is the arithmetic-only interpreter
+    lib.calls.clear()
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    kept = K.sin_op_dyn(a, p)            # (an unreferenced recorded result is never launched)
+    K.gt_op_dyn(a, b, p)
+    p.finish()
+    assert sorted(n for n, _ in lib.launched()) == ["agpu_fused_chain", "agpu_fused_chain"]
+    # the predicate first: it is launched at once, there is nothing to pair the later value chain with
+    lib.calls.clear()
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    K.gt_op_dyn(a, b, p)
+    kept2 = K.add_op_dyn(a, b, p)
+    p.finish()
+    assert sorted(n for n, _ in lib.launched()) == ["agpu_fused_chain", "agpu_fused_chain"]
+    assert s.len == a.len == kept.len == kept2.len
+
+
+def test_absorbed_and_foreign_source_chains_are_not_paired(stub):
+    lib, dev = stub
+    a, b, c = f32(dev), f32(dev), f32(dev)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    s = K.add_op_dyn(a, b, p)
+    t = K.mul_op_dyn(s, c, p)            # absorbs s: the pending chain is [add b, mul c] over a
+    g = K.lt_op_dyn(a, c, p)             # pairs with t's chain (same source a)
+    (name, steps), = lib.launched()
+    assert name == "agpu_fused_chain_pair" and len(steps) == 5 and t._lazy is None
+    assert s._lazy is not None and s._lazy.consumed          # s itself stays unlaunched unless somebody reads it
+    lib.calls.clear()
+    K.eq_op_dyn(b, c, p)                 # source b: no pending chain starts there
+    assert [n for n, _ in lib.launched()] == ["agpu_fused_chain"]
+    p.finish()
+    assert isinstance(g, ag.BooleanArrayGPU)
+
+
+def test_pair_eligibility_rules(stub):
+    _lib, dev = stub
+    a, b, c, d, e = (f32(dev) for _ in range(5))
+    assert K.pair_eligible(a, [("add", b)], [("gt", b)])
+    assert K.pair_eligible(a, [("mul", b), ("add", c)], [("sub", d), ("lteq", b)])          # 3 distinct columns
+    assert not K.pair_eligible(a, [("mul", b), ("add", c)], [("sub", d), ("lteq", e)])      # 4
+    assert not K.pair_eligible(a, [("add", b)], [("add", b)])                                # no closing compare
+    assert not K.pair_eligible(a, [("gt", b)], [("gt", b)])                                  # compare in the value chain
+    assert not K.pair_eligible(a, [("power", b)], [("gt", b)])
+    assert not K.pair_eligible(a, [("abs",)] * 4, [("neg",)] * 2 + [("eq", 1.0)])            # 4 + 3 + 2 > 8 steps
+    assert K.pair_eligible(a, [("abs",)] * 3, [("neg",)] * 2 + [("eq", 1.0)])
+    i = ag.Int8ArrayGPU.from_slice([1] * 64, dev)
+    assert not K.pair_eligible(i, [("add", 1.0)], [("gt", 0.0)])                             # f32 sources only
+    with pytest.raises(ag.Panic):
+        K.fused_chain_pair(a, [("power", b)], [("gt", b)])
+
+
+def test_a_predicate_that_reads_the_pending_value_is_not_paired_with_it(stub):
+    lib, dev = stub
+    a, b = f32(dev), f32(dev)
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    s = K.add_op_dyn(a, b, p)
+    g = K.gt_op_dyn(a, s, p)             # needs s: s is launched first, then the compare
+    p.finish()
+    assert [n for n, _ in lib.launched()] == ["agpu_fused_chain", "agpu_fused_chain"]
+    assert s._lazy is None and isinstance(g, ag.BooleanArrayGPU)
+    # ... also when the dependency is indirect (an operand chain that has s as a column)
+    lib.calls.clear()
+    p = ag.ArrowComputePipeline(dev, fuse=True)
+    s = K.add_op_dyn(a, b, p)
+    t = K.mul_op_dyn(b, s, p)            # chain over b with s as operand column
+    g = K.gt_op_dyn(a, t, p)
+    p.finish()
+    assert "agpu_fused_chain_pair" not in [n for n, _ in lib.launched()]
+    assert len(lib.launched()) == 3
