@@ -16,6 +16,7 @@
 // `throw arrow_gpu::Panic`.  Every `x_op(.., pipeline)` enqueues one kernel on the device's
 // stream; `x(..)` is the reference's default_impl! (new pipeline, op, finish).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -685,6 +686,41 @@ std::variant<Float32ArrayGPU, BooleanArrayGPU> fused_chain(const PrimitiveArrayG
   if (rc == AGPU_EUNSUPPORTED || rc == AGPU_EINVAL) throw Panic("fused_chain: unsupported chain");
   check(rc, "fused_chain");
   return out;
+}
+
+// A value chain and a predicate chain of ONE source column in one kernel (agpu_fused_chain_pair),
+// e.g. s = a + b; g = a > b:  fused_chain_pair(a, {binary(AGPU_ADD, b)}, {compare(AGPU_GT, b)}).
+// Both chains must depend on the same validity bitmaps; the two results share one bitmap buffer.
+inline std::pair<Float32ArrayGPU, BooleanArrayGPU> fused_chain_pair(const Float32ArrayGPU& a, const std::vector<ChainStep>& value_steps,
+                                                                   const std::vector<ChainStep>& pred_steps) {
+  auto bitmaps = [&](const std::vector<ChainStep>& steps) {
+    std::vector<const uint32_t*> v;
+    if (a.null_buffer) v.push_back(vptr(a.null_buffer));
+    for (const auto& s : steps)
+      if (s.has_validity) v.push_back(s.raw.validity);
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    return v;
+  };
+  const auto vb = bitmaps(value_steps);
+  if (vb != bitmaps(pred_steps)) throw Panic("fused_chain_pair: the two chains depend on different validity bitmaps");
+  std::vector<agpu_chain_step> raw;
+  for (const auto& s : value_steps) raw.push_back(s.raw);
+  agpu_chain_step mark{};
+  mark.kind = AGPU_STEP_STORE;
+  raw.push_back(mark);
+  mark.kind = AGPU_STEP_RESET;
+  raw.push_back(mark);
+  for (const auto& s : pred_steps) raw.push_back(s.raw);
+  Validity nb;
+  if (!vb.empty()) nb = NullBitBufferGpu{std::make_shared<ArrowGpuBuffer>(a.gpu_device, bitmap_words(a.len) * 4), a.len, a.gpu_device};
+  auto value = Float32ArrayGPU::empty(a.len, a.gpu_device, nb);
+  auto pred = BooleanArrayGPU::empty(a.len, a.gpu_device, nb);
+  int rc = agpu_fused_chain_pair(a.gpu_device->handle(), AGPU_F32, a.data->ptr(), vptr(a.null_buffer), raw.data(), (int)raw.size(),
+                                 (float*)value.data->ptr(), (uint32_t*)pred.data->ptr(), a.len, vptr_mut(value.null_buffer));
+  if (rc == AGPU_EUNSUPPORTED || rc == AGPU_EINVAL) throw Panic("fused_chain_pair: unsupported pair of chains");
+  check(rc, "fused_chain_pair");
+  return {value, pred};
 }
 
 // the same chain on an INTEGER column (agpu_fused_chain_int): operands are columns or one-element

@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
     return 0;
   }
   if (json) std::printf("{\"what\": \"C++ host mirror (arrow_gpu.hpp), f32 add + gt with null bitmaps, cold inputs (rotating copies >= 512 MiB), "
-                        "wall clock over >= 512 submissions; frac = algorithmic GB/s / 6541.1\", \"sizes\": {");
+                        "wall clock over >= 512 submissions; frac = algorithmic GB/s / 6541.1; fused_pair = add + gt as ONE kernel (agpu_fused_chain_pair), per PROGRAM\", \"sizes\": {");
   bool first_size = true;
   std::mt19937 rng(1);
   std::uniform_real_distribution<float> dist(-1000.f, 1000.f);
@@ -113,16 +113,32 @@ int main(int argc, char** argv) {
     device->sync();
     const double us_g = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / (2.0 * pairs);
     const double gbs_g = (12.375 + 8.5) / 2.0 * double(n) / us_g / 1e3;
+    // both results out of ONE kernel (agpu_fused_chain_pair): a and b read once, one launch per program
+    for (size_t k = 0; k < std::min<size_t>(copies, 8); ++k)
+      fused_chain_pair(as[k], {ChainStep::binary(AGPU_ADD, bs[k])}, {ChainStep::compare(AGPU_GT, bs[k])});
+    device->sync();
+    t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < rounds; ++r)
+      for (size_t k = 0; k < copies; ++k)
+        auto sg = fused_chain_pair(as[k], {ChainStep::binary(AGPU_ADD, bs[k])}, {ChainStep::compare(AGPU_GT, bs[k])});
+    device->sync();
+    const double us_p = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / pairs;  // per PROGRAM
+    const double gbs_p = 12.5 * double(n) / us_p / 1e3;                   // what this kernel moves
+    const double gbs_pu = (12.375 + 8.5) * double(n) / us_p / 1e3;        // what the two separate ops would have moved
     if (json) {
       std::printf("%s\"%zu rows\": {\"eager_us_per_op\": %.3f, \"eager_GBps\": %.1f, \"eager_frac_measured_peak\": %.4f, "
-                  "\"captured_us_per_op\": %.3f, \"captured_GBps\": %.1f, \"captured_frac_measured_peak\": %.4f, \"input_copies\": %zu}",
-                  first_size ? "" : ", ", n, us, gbs, gbs / 6541.1, us_g, gbs_g, gbs_g / 6541.1, copies);
+                  "\"captured_us_per_op\": %.3f, \"captured_GBps\": %.1f, \"captured_frac_measured_peak\": %.4f, "
+                  "\"fused_pair_us_per_program\": %.3f, \"fused_pair_frac_measured_peak\": %.4f, \"fused_pair_frac_of_unfused_bytes\": %.4f, "
+                  "\"input_copies\": %zu}",
+                  first_size ? "" : ", ", n, us, gbs, gbs / 6541.1, us_g, gbs_g, gbs_g / 6541.1, us_p, gbs_p / 6541.1, gbs_pu / 6541.1, copies);
       first_size = false;
       continue;
     }
-    std::printf("rows=2^%d  copies=%zu  eager %.2f us per op  %.0f GB/s (%.3f of 6541) | captured %.2f us per op  %.0f GB/s (%.3f of 6541)  "
+    std::printf("rows=2^%d  copies=%zu  eager %.2f us per op  %.0f GB/s (%.3f of 6541) | captured %.2f us per op  %.0f GB/s (%.3f of 6541) | "
+                "add+gt as one kernel %.2f us per program  %.3f of 6541 on its own 12.5 B/row, %.3f counting the 20.875 B/row of the two ops  "
                 "[mean of add and gt, validity included; %llu kernels per submit]\n", (int)std::log2((double)n), copies, us, gbs,
-                gbs / 6541.1, us_g, gbs_g, gbs_g / 6541.1, (unsigned long long)progs[0]->kernels_per_submit());
+                gbs / 6541.1, us_g, gbs_g, gbs_g / 6541.1, us_p, gbs_p / 6541.1, gbs_pu / 6541.1,
+                (unsigned long long)progs[0]->kernels_per_submit());
   }
   if (json) std::printf("}}\n");
   return 0;

@@ -148,6 +148,23 @@ int main() {
     CHECK(std::get<BooleanArrayGPU>(chained).raw_values() == ga.mul(gb).add(gc).gt(gd).raw_values());
     auto chain_vals = fused_chain(Int8ArrayGPU::from_slice({0, 1, 4, 9, -16}, device), {ChainStep::unary(AGPU_ABS), ChainStep::unary(AGPU_SQRT), ChainStep::binary(AGPU_MUL, 2.0f)});
     CHECK(feq(std::get<Float32ArrayGPU>(chain_vals).raw_values(), {0, 2, 4, 6, 8}));
+    {  // s = a + b and g = a > b out of one kernel; the interpreter path (min) and a third column too
+      auto pa = Float32ArrayGPU::from_optional_slice({1.5f, None, -3.0f, 4.0f, 1e30f, -0.0f, 7.0f}, device);
+      auto pb = Float32ArrayGPU::from_optional_slice({1.5f, 2.0f, None, -4.0f, 1e30f, 0.0f, 8.0f}, device);
+      auto pc = Float32ArrayGPU::from_slice({0.f, 0.f, 0.f, 5.f, 0.f, 0.f, 7.f}, device);
+      auto [ps, pg] = fused_chain_pair(pa, {ChainStep::binary(AGPU_ADD, pb)}, {ChainStep::compare(AGPU_GT, pb)});
+      CHECK(ps.values() == pa.add(pb).values());
+      CHECK(pg.values() == pa.gt(pb).values());
+      auto [qs, qg] = fused_chain_pair(pa, {ChainStep::binary(AGPU_MIN, pb), ChainStep::binary(AGPU_MUL, 2.0f)}, {ChainStep::unary(AGPU_ABS), ChainStep::compare(AGPU_LTEQ, pb)});
+      CHECK(qs.values() == pa.min(pb).mul_scalar(Float32ArrayGPU::from_slice({2.0f}, device)).values());
+      CHECK(qg.values() == pa.abs().lteq(pb).values());
+      auto [rs, rg] = fused_chain_pair(pc, {ChainStep::binary(AGPU_SUB, pc)}, {ChainStep::compare(AGPU_EQ, 7.0f)});
+      CHECK(feq(rs.raw_values(), {0, 0, 0, 0, 0, 0, 0}));
+      CHECK((rg.raw_values() == std::vector<bool>{false, false, false, false, false, false, true}));
+      bool refused = false;   // g would depend on pb's bitmap, s would not
+      try { fused_chain_pair(pc, {ChainStep::binary(AGPU_ADD, pc)}, {ChainStep::compare(AGPU_GT, pb)}); } catch (const Panic&) { refused = true; }
+      CHECK(refused);
+    }
     // dyn layer incl. the recording forms, broadcast, bitcast and put
     {
       ArrowComputePipeline pipe(device, "dyn");
