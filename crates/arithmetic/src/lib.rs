@@ -386,3 +386,45 @@ pub fn fused_mul_add_gt_op(
     );
     out
 }
+
+// ---------------------------------------------------------------------------------------------
+// new surface (BASELINE.json config 1): the reference's first benchmark program
+//     let s = a.add_op(&b, p);  let g = a.gt_op(&b, p);
+// as ONE kernel: `value = a binop b`, `predicate = a cmpop c` (c is usually b) read every column
+// once (12.5 B/row instead of 20.875) and are one launch instead of two; both results are
+// bit-identical to the separate ops.  binop: AGPU_ADD / SUB / MUL / DIV (dedicated kernel) or
+// AGPU_REM / MIN / MAX (chain interpreter); cmpop: AGPU_GT .. AGPU_EQ.  The kernel writes ONE
+// validity bitmap (AND of a, b, c), so b and c must either both carry one or both carry none;
+// the predicate's bitmap is a device-side copy of it (buffers are uniquely owned here).
+// ---------------------------------------------------------------------------------------------
+pub fn fused_binary_compare_op(
+    a: &Float32ArrayGPU, binop: c_int, b: &Float32ArrayGPU, cmpop: c_int, c: &Float32ArrayGPU, _pipeline: &mut ArrowComputePipeline,
+) -> (Float32ArrayGPU, BooleanArrayGPU) {
+    assert!(a.len == b.len && a.len == c.len, "fused_binary_compare_op: length mismatch");
+    let same_column = std::ptr::eq(b.values_ptr(), c.values_ptr());
+    assert!(same_column || b.null_buffer.is_some() == c.null_buffer.is_some(),
+            "fused_binary_compare_op: value and predicate would depend on different validity bitmaps");
+    let step = |kind: c_int, op: c_int, col: Option<&Float32ArrayGPU>| AgpuChainStep {
+        kind, op,
+        operand: col.map_or(std::ptr::null(), |x| x.values_ptr()),
+        validity: col.map_or(std::ptr::null(), |x| x.validity_ptr()),
+        scalar: 0.0,
+    };
+    let steps = [step(AGPU_STEP_BINARY_COLUMN, binop, Some(b)), step(AGPU_STEP_STORE, 0, None), step(AGPU_STEP_RESET, 0, None),
+                 step(AGPU_STEP_COMPARE_COLUMN, cmpop, Some(c))];
+    let nb = NullBitBufferGpu::for_output(&a.gpu_device, a.len, &[a.null_buffer.as_ref(), b.null_buffer.as_ref(), c.null_buffer.as_ref()]);
+    let value = Float32ArrayGPU::new_empty(&a.gpu_device, a.len, nb);
+    let bits = BooleanArrayGPU::new_empty(&a.gpu_device, a.len, None);
+    let rc = unsafe {
+        agpu_fused_chain_pair(a.gpu_device.handle(), AGPU_F32, a.values_ptr(), a.validity_ptr(), steps.as_ptr(), steps.len() as c_int,
+                              value.data.ptr() as *mut f32, bits.data.ptr() as *mut u32, a.len,
+                              NullBitBufferGpu::words_mut(value.null_buffer.as_ref()))
+    };
+    if rc == AGPU_EUNSUPPORTED || rc == AGPU_EINVAL {
+        panic!("fused_binary_compare_op: unsupported operator pair {binop} / {cmpop}");
+    }
+    check(rc, "fused_binary_compare_op");
+    let predicate = BooleanArrayGPU { null_buffer: NullBitBufferGpu::clone_null_bit_buffer(&value.null_buffer), ..bits };
+    (value, predicate)
+}
+
