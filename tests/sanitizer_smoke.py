@@ -59,6 +59,13 @@ def main():
         m.any(), m.all(), m.bitwise_not(), m.take(ag.UInt32ArrayGPU.from_numpy(idx, None, dev))
         # fused chains: f32 interpreter, integer packed-word interpreter (value + predicate), u16 filter
         K.fused_chain(fa, [("abs",), ("sqrt",), ("mul", fa), ("lteq", fa)])
+        # two results in one pass: the dedicated binop | compare kernel and the interpreter form
+        fb = ag.Float32ArrayGPU.from_numpy(f[::-1].copy(), va, dev)
+        pv, pp = K.fused_chain_pair(fa, [("add", fb)], [("gt", fb)])
+        assert np.array_equal(pv.raw_values().view(np.uint32), fa.add(fb).raw_values().view(np.uint32))
+        assert np.array_equal(pp.raw_values(), fa.gt(fb).raw_values())
+        pv, pp = K.fused_chain_pair(fa, [("abs",), ("min", fb)], [("mul", 2.0), ("lteq", fb)])
+        assert np.array_equal(pp.raw_values(), fa.mul_scalar(ag.Float32ArrayGPU.from_slice([2.0], dev)).lteq(fb).raw_values())
         s8 = ag.Int8ArrayGPU.from_slice([3], dev)
         got = K.fused_chain_int(a, [("add", b), ("bitwise_and", b), ("mul", K.DeviceScalar(s8))])
         assert np.array_equal(got.raw_values(), a.add(b).bitwise_and(b).mul_scalar(s8).raw_values())
