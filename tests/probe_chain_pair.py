@@ -18,7 +18,9 @@ for n in (1 << 24, 1 << 28):
     cases = {"add (12.375 B/row)": (lambda: a.add(b), 12.375), "gt (8.5)": (lambda: a.gt(b), 8.5),
              "chain [add b] (12.375)": (lambda: K.fused_chain(a, [("add", b)]), 12.375),
              "chain [gt b] (8.5)": (lambda: K.fused_chain(a, [("gt", b)]), 8.5),
-             "pair add | gt (12.5)": (lambda: K.fused_chain_pair(a, [("add", b)], [("gt", b)]), 12.5)}
+             "pair add | gt (12.5)": (lambda: K.fused_chain_pair(a, [("add", b)], [("gt", b)]), 12.5),
+             "pair min | gt, interpreter (12.5)": (lambda: K.fused_chain_pair(a, [("min", b)], [("gt", b)]), 12.5),
+             "chain [mul b, add b, sub 1.0] (12.375)": (lambda: K.fused_chain(a, [("mul", b), ("add", b), ("sub", 1.0)]), 12.375)}
     reps = 30 if n == 1 << 24 else 8
     for name, (fn, bpr) in cases.items():
         keep = [fn(), fn(), fn()]      # three live results: the timed loop finds its blocks in the cache
