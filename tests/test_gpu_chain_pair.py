@@ -54,7 +54,7 @@ def test_pair_equals_the_two_chains_run_separately(prog, validity, device):
     """validity "source": only the source column has a bitmap; "all": every column has one — then
     the two chains of some programs depend on different bitmaps and must be refused"""
     rng = np.random.default_rng(50 + prog)
-    for n in (1, 5, 33, 1023, 4097, 70001, (1 << 20) + 3):
+    for n in (0, 1, 5, 33, 1023, 4097, 70001, (1 << 20) + 3):
         a, _, _ = column(rng, n, validity != "none", device)
         cols = {k: column(rng, n, validity == "all", device, -4, 4)[0] for k in "BCD"}
         cols["S"] = ag.Float32ArrayGPU.from_slice([1.25], device)
