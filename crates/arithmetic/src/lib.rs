@@ -29,7 +29,7 @@ pub trait ArrowScalarAdd<Rhs>: ArrayUtils {
     fn add_scalar_op(&self, value: &Rhs, pipeline: &mut ArrowComputePipeline) -> Self::Output;
 }
 
-/// The subtract operator ArrowArray - Scalar
+/// column − one-element column
 pub trait ArrowScalarSub<Rhs>: ArrayUtils {
     type Output;
     fn sub_scalar(&self, value: &Rhs) -> Self::Output {
@@ -65,7 +65,7 @@ pub trait ArrowScalarRem<Rhs>: ArrayUtils {
     fn rem_scalar_op(&self, value: &Rhs, pipeline: &mut ArrowComputePipeline) -> Self::Output;
 }
 
-/// The addition operator ArrowArray + ArrowArray
+/// column + column
 pub trait ArrowAdd<Rhs>: ArrayUtils {
     type Output;
     fn add(&self, value: &Rhs) -> Self::Output {
@@ -74,7 +74,7 @@ pub trait ArrowAdd<Rhs>: ArrayUtils {
     fn add_op(&self, value: &Rhs, pipeline: &mut ArrowComputePipeline) -> Self::Output;
 }
 
-/// The subtract operator ArrowArray - ArrowArray
+/// column − column
 pub trait ArrowSub<Rhs>: ArrayUtils {
     type Output;
     fn sub(&self, value: &Rhs) -> Self::Output {
@@ -92,7 +92,7 @@ pub trait ArrowMul<Rhs>: ArrayUtils {
     fn mul_op(&self, value: &Rhs, pipeline: &mut ArrowComputePipeline) -> Self::Output;
 }
 
-/// The division operator ArrowArray / ArrowArray
+/// column ÷ column
 pub trait ArrowDiv<Rhs>: ArrayUtils {
     type Output;
     fn div(&self, value: &Rhs) -> Self::Output {

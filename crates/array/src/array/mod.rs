@@ -107,20 +107,20 @@ pub type Date32ArrayGPU = PrimitiveArrayGpu<Date32Type>;
 pub mod types {
     use super::Date32Type;
 
-    /// Arrow Array backed by i32
+    /// column of i32 rows
     pub trait Int32Type {}
     impl Int32Type for i32 {}
     impl Int32Type for Date32Type {}
 
-    /// Arrow Array backed by f32
+    /// column of f32 rows
     pub trait Float32Type {}
     impl Float32Type for f32 {}
 
-    /// Arrow Array backed by u32
+    /// column of u32 rows
     pub trait UInt32Type {}
     impl UInt32Type for u32 {}
 
-    /// Arrow Array backed by u16
+    /// column of u16 rows
     pub trait UInt16Type {}
     impl UInt16Type for u16 {}
 }

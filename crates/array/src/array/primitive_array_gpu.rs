@@ -14,7 +14,7 @@ pub struct PrimitiveArrayGpu<T: ArrowPrimitiveType> {
     pub data: ArrowGpuBuffer,
     pub gpu_device: Arc<GpuDevice>,
     pub phantom: PhantomData<T>,
-    /// Actual len of the array
+    /// number of rows (not bytes)
     pub len: usize,
     pub null_buffer: Option<NullBitBufferGpu>,
 }

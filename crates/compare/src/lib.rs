@@ -21,7 +21,7 @@ macro_rules! eager {
 /// Marker of the element types that can be compared (the reference's helper carried shader text)
 pub trait CompareType {}
 
-/// Trait for comparing ArrowArrays
+/// Row-wise comparisons producing a `BooleanArrayGPU` (compare/src/lib.rs:41-62 of the reference)
 pub trait Compare: ArrayUtils {
     fn gt(&self, operand: &Self) -> BooleanArrayGPU {
         eager!(self, gt_op, operand)

@@ -20,7 +20,7 @@ pub trait LogicalType {}
 macro_rules! mark { ($($t:ty),*) => { $(impl LogicalType for $t {})* }; }
 mark!(u32, u16, u8, i32, i16, i8);
 
-/// Trait for logical operation on each element of the array
+/// Bitwise logic and per-row shifts, row by row (logical/src/lib.rs:44-86 of the reference)
 pub trait Logical: ArrayUtils + Sized {
     fn bitwise_and(&self, operand: &Self) -> Self {
         eager!(self, bitwise_and_op, operand)
@@ -247,7 +247,7 @@ dyn_shift!(
      bitwise_shr_dyn, bitwise_shr_op_dyn, bitwise_shr_op]
 );
 
-/// Compute !x for each x in array
+/// `!x` for every row
 pub fn bitwise_not_dyn(data: &ArrowArrayGPU) -> ArrowArrayGPU {
     let mut pipeline = ArrowComputePipeline::new(data.get_gpu_device(), None);
     let result = bitwise_not_op_dyn(data, &mut pipeline);

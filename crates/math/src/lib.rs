@@ -169,7 +169,7 @@ dyn_unary!(
      log2_dyn, log2_op_dyn, log2_op, Float32ArrayGPU]
 );
 
-/// Compute x ^ y for each pair (x, y) in zip(self, other)
+/// `x` to the power `y`, row by row over `self` and `other`
 pub fn power_dyn(data_1: &ArrowArrayGPU, data_2: &ArrowArrayGPU) -> ArrowArrayGPU {
     let mut pipeline = ArrowComputePipeline::new(data_1.get_gpu_device(), None);
     let result = power_op_dyn(data_1, data_2, &mut pipeline);

@@ -7,7 +7,7 @@ use arrow_gpu_array::array::*;
 use arrow_gpu_array::gpu_utils::ffi::*;
 use arrow_gpu_array::gpu_utils::ArrowComputePipeline;
 
-/// Trait for swizzle operations on the array
+/// Row re-arrangement: merge, take, put — and filter (routines/src/lib.rs:28-72 of the reference)
 pub trait Swizzle: ArrayUtils + Sized {
     fn merge(&self, other: &Self, mask: &BooleanArrayGPU) -> Self {
         let mut pipeline = ArrowComputePipeline::new(self.get_gpu_device(), None);
@@ -32,7 +32,7 @@ pub trait Swizzle: ArrayUtils + Sized {
     /// Elements of self where the mask bit is set, else of other; None in mask results in None
     fn merge_op(&self, other: &Self, mask: &BooleanArrayGPU, pipeline: &mut ArrowComputePipeline) -> Self;
 
-    /// Creates a new array by taking elements from self using the indexes
+    /// gathers `self[indexes[i]]` into a new column of `indexes.len` rows
     fn take_op(&self, indexes: &UInt32ArrayGPU, pipeline: &mut ArrowComputePipeline) -> Self;
 
     /// Put elements from self using src_indexes into dst using dst_indexes

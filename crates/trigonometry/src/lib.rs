@@ -16,7 +16,7 @@ macro_rules! eager {
     }};
 }
 
-/// Trait for hyperbolic operation on each element of the array
+/// `sinh`, row by row (trigonometry/src/lib.rs:22-33 of the reference)
 pub trait Hyperbolic: ArrayUtils {
     type Output;
     fn sinh(&self) -> Self::Output {
@@ -25,7 +25,7 @@ pub trait Hyperbolic: ArrayUtils {
     fn sinh_op(&self, pipeline: &mut ArrowComputePipeline) -> Self::Output;
 }
 
-/// Trait for trigonometry operation on each element of the array
+/// `cos`, `sin`, `acos`, row by row (trigonometry/src/lib.rs:49-68 of the reference)
 pub trait Trigonometric: ArrayUtils {
     type Output;
     fn cos(&self) -> Self::Output {
