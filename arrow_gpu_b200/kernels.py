@@ -251,15 +251,15 @@ def _dyn1(method_name, doc=""):
     return dyn, op_dyn
 
 
-add_scalar_dyn, add_scalar_op_dyn = _dyn2("add_scalar_op", "Add a scalar to each element in the array")
-sub_scalar_dyn, sub_scalar_op_dyn = _dyn2("sub_scalar_op", "Subtract a scalar from each element in the array")
-mul_scalar_dyn, mul_scalar_op_dyn = _dyn2("mul_scalar_op", "Multiply a scalar to each element in the array")
-div_scalar_dyn, div_scalar_op_dyn = _dyn2("div_scalar_op", "Divide each element in the array by scalar")
-rem_scalar_dyn, rem_scalar_op_dyn = _dyn2("rem_scalar_op", "Find remainder of each element in the array by scalar")
-add_array_dyn, add_array_op_dyn = _dyn2("add_op", "Compute x + y for each pair (x, y) in zip(lhs, rhs)")
-sub_array_dyn, sub_array_op_dyn = _dyn2("sub_op", "Compute x - y for each pair (x, y) in zip(lhs, rhs)")
-mul_array_dyn, mul_array_op_dyn = _dyn2("mul_op", "Compute x * y for each pair (x, y) in zip(lhs, rhs)")
-div_array_dyn, div_array_op_dyn = _dyn2("div_op", "Compute x / y for each pair (x, y) in zip(lhs, rhs)")
+add_scalar_dyn, add_scalar_op_dyn = _dyn2("add_scalar_op", "column + one-element column (the reference's scalar form)")
+sub_scalar_dyn, sub_scalar_op_dyn = _dyn2("sub_scalar_op", "column - one-element column")
+mul_scalar_dyn, mul_scalar_op_dyn = _dyn2("mul_scalar_op", "column * one-element column")
+div_scalar_dyn, div_scalar_op_dyn = _dyn2("div_scalar_op", "column / one-element column")
+rem_scalar_dyn, rem_scalar_op_dyn = _dyn2("rem_scalar_op", "column % one-element column")
+add_array_dyn, add_array_op_dyn = _dyn2("add_op", "x + y, row by row over both columns")
+sub_array_dyn, sub_array_op_dyn = _dyn2("sub_op", "x - y, row by row over both columns")
+mul_array_dyn, mul_array_op_dyn = _dyn2("mul_op", "x * y, row by row over both columns")
+div_array_dyn, div_array_op_dyn = _dyn2("div_op", "x / y, row by row over both columns")
 neg_dyn, neg_op_dyn = _dyn1("neg_op")
 
 
@@ -306,11 +306,11 @@ for _n, _o in _CMP.items():
     setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)     # Compare::gt_op ...
     setattr(PrimitiveArrayGpu, _n, _eager(_fn))      # Compare::gt ...
 
-gt_dyn, gt_op_dyn = _dyn2("gt_op", "Construct bool array from computing x > y for each pair (x, y)")
-gteq_dyn, gteq_op_dyn = _dyn2("gteq_op", "Construct bool array from computing x >= y for each pair (x, y)")
-lt_dyn, lt_op_dyn = _dyn2("lt_op", "Construct bool array from computing x < y for each pair (x, y)")
-lteq_dyn, lteq_op_dyn = _dyn2("lteq_op", "Construct bool array from computing x <= y for each pair (x, y)")
-eq_dyn, eq_op_dyn = _dyn2("eq_op", "Construct bool array from computing x == y for each pair (x, y)")
+gt_dyn, gt_op_dyn = _dyn2("gt_op", "row-wise predicate x > y -> BooleanArrayGPU")
+gteq_dyn, gteq_op_dyn = _dyn2("gteq_op", "row-wise predicate x >= y -> BooleanArrayGPU")
+lt_dyn, lt_op_dyn = _dyn2("lt_op", "row-wise predicate x < y -> BooleanArrayGPU")
+lteq_dyn, lteq_op_dyn = _dyn2("lteq_op", "row-wise predicate x <= y -> BooleanArrayGPU")
+eq_dyn, eq_op_dyn = _dyn2("eq_op", "row-wise predicate x == y -> BooleanArrayGPU")
 
 
 def _make_minmax(name, op):
@@ -326,8 +326,8 @@ for _n, _o in {"min": _ffi.MIN, "max": _ffi.MAX}.items():
     setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)     # MinMax::min_op / max_op
     setattr(PrimitiveArrayGpu, _n, _eager(_fn))
 
-min_dyn, min_op_dyn = _dyn2("min_op", "Compute min(x, y) for each pair (x, y) in zip(lhs, rhs)")
-max_dyn, max_op_dyn = _dyn2("max_op", "Compute max(x, y) for each pair (x, y) in zip(lhs, rhs)")
+min_dyn, min_op_dyn = _dyn2("min_op", "min(x, y), row by row over both columns")
+max_dyn, max_op_dyn = _dyn2("max_op", "max(x, y), row by row over both columns")
 
 # ==========================================================================================
 # logical  (crates/logical/src/lib.rs, boolean.rs)
@@ -427,12 +427,12 @@ def _bool_reduce(fn_name):
 BooleanArrayGPU.any = _bool_reduce("agpu_any")
 BooleanArrayGPU.all = _bool_reduce("agpu_all")
 
-bitwise_and_dyn, bitwise_and_op_dyn = _dyn2("bitwise_and_op", "Compute x & y for each pair (x, y)")
-bitwise_or_dyn, bitwise_or_op_dyn = _dyn2("bitwise_or_op", "Compute x | y for each pair (x, y)")
-bitwise_xor_dyn, bitwise_xor_op_dyn = _dyn2("bitwise_xor_op", "Compute x ^ y for each pair (x, y)")
-bitwise_shl_dyn, bitwise_shl_op_dyn = _dyn2("bitwise_shl_op", "Compute x << y for each pair (x, y)")
-bitwise_shr_dyn, bitwise_shr_op_dyn = _dyn2("bitwise_shr_op", "Compute x >> y for each pair (x, y)")
-bitwise_not_dyn, bitwise_not_op_dyn = _dyn1("bitwise_not_op", "Compute !x for each x in array")
+bitwise_and_dyn, bitwise_and_op_dyn = _dyn2("bitwise_and_op", "x & y, row by row over both columns")
+bitwise_or_dyn, bitwise_or_op_dyn = _dyn2("bitwise_or_op", "x | y, row by row over both columns")
+bitwise_xor_dyn, bitwise_xor_op_dyn = _dyn2("bitwise_xor_op", "x ^ y, row by row over both columns")
+bitwise_shl_dyn, bitwise_shl_op_dyn = _dyn2("bitwise_shl_op", "x << y, row by row over both columns")
+bitwise_shr_dyn, bitwise_shr_op_dyn = _dyn2("bitwise_shr_op", "x >> y, row by row over both columns")
+bitwise_not_dyn, bitwise_not_op_dyn = _dyn1("bitwise_not_op", "!x of every row")
 
 # ==========================================================================================
 # cast  (crates/cast/src/lib.rs)
@@ -476,8 +476,8 @@ for _cls in (PrimitiveArrayGpu, BooleanArrayGPU):
 PrimitiveArrayGpu.bitcast_op = _bitcast_op
 PrimitiveArrayGpu.bitcast = _eager(_bitcast_op)
 
-cast_dyn, cast_op_dyn = _dyn2("cast_op", "Cast x as `T` for each x in array")
-bitcast_dyn, bitcast_op_dyn = _dyn2("bitcast_op", "Reinterpret x as `T` for each x in array")
+cast_dyn, cast_op_dyn = _dyn2("cast_op", "every row converted to the element type `T`")
+bitcast_dyn, bitcast_op_dyn = _dyn2("bitcast_op", "the same bits of every row read as `T`")
 
 # ==========================================================================================
 # math  (crates/math/src/lib.rs)   trigonometry  (crates/trigonometry/src/lib.rs)
@@ -517,14 +517,14 @@ PrimitiveArrayGpu.abs = _eager(_abs_op)
 PrimitiveArrayGpu.power_op = _power_op
 PrimitiveArrayGpu.power = _eager(_power_op)
 
-abs_dyn, abs_op_dyn = _dyn1("abs_op", "Compute abs(x) for each x in array")
-sqrt_dyn, sqrt_op_dyn = _dyn1("sqrt_op", "Compute square_root(x) for each x in array")
-cbrt_dyn, cbrt_op_dyn = _dyn1("cbrt_op", "Compute cube_root(x) for each x in array")
-exp_dyn, exp_op_dyn = _dyn1("exp_op", "Compute e^x for each x in array")
-exp2_dyn, exp2_op_dyn = _dyn1("exp2_op", "Compute 2^x for each x in array")
-log_dyn, log_op_dyn = _dyn1("log_op", "Compute log(x) for each x in array")
-log2_dyn, log2_op_dyn = _dyn1("log2_op", "Compute log_to_base_2(x) for each x in array")
-power_dyn, power_op_dyn = _dyn2("power_op", "Compute x ^ y for each pair (x, y) in zip(self, other)")
+abs_dyn, abs_op_dyn = _dyn1("abs_op", "abs(x) of every row")
+sqrt_dyn, sqrt_op_dyn = _dyn1("sqrt_op", "square_root(x) of every row")
+cbrt_dyn, cbrt_op_dyn = _dyn1("cbrt_op", "cube_root(x) of every row")
+exp_dyn, exp_op_dyn = _dyn1("exp_op", "e^x of every row")
+exp2_dyn, exp2_op_dyn = _dyn1("exp2_op", "2^x of every row")
+log_dyn, log_op_dyn = _dyn1("log_op", "log(x) of every row")
+log2_dyn, log2_op_dyn = _dyn1("log2_op", "log_to_base_2(x) of every row")
+power_dyn, power_op_dyn = _dyn2("power_op", "x ^ y, row by row over both columns")
 
 _TRIG_INT = (Int8ArrayGPU, UInt8ArrayGPU, Int16ArrayGPU, UInt16ArrayGPU)
 
@@ -544,10 +544,10 @@ for _n, _o, _ai in (("sin", _ffi.SIN, True), ("cos", _ffi.COS, True), ("acos", _
     setattr(PrimitiveArrayGpu, f"{_n}_op", _fn)    # Trigonometric::sin_op ..., Hyperbolic::sinh_op
     setattr(PrimitiveArrayGpu, _n, _eager(_fn))
 
-sin_dyn, sin_op_dyn = _dyn1("sin_op", "Compute sin(x) for each x in array")
-cos_dyn, cos_op_dyn = _dyn1("cos_op", "Compute cos(x) for each x in array")
-acos_dyn, acos_op_dyn = _dyn1("acos_op", "Compute acos(x) for each x in array")
-sinh_dyn, sinh_op_dyn = _dyn1("sinh_op", "Compute sinh(x) for each x in array")
+sin_dyn, sin_op_dyn = _dyn1("sin_op", "sin(x) of every row")
+cos_dyn, cos_op_dyn = _dyn1("cos_op", "cos(x) of every row")
+acos_dyn, acos_op_dyn = _dyn1("acos_op", "acos(x) of every row")
+sinh_dyn, sinh_op_dyn = _dyn1("sinh_op", "sinh(x) of every row")
 
 # ==========================================================================================
 # routines  (crates/routines/src/lib.rs, merge.rs, take.rs, put.rs, bool.rs)
