@@ -291,37 +291,37 @@ macro_rules! dyn_pair {
     };
 }
 
-dyn_pair!(/// Add a scalar to each element in the array
+dyn_pair!(/// column + one-element column
           add_scalar_dyn, add_scalar_op_dyn, add_scalar_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, Date32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU],
           mixed: [[Int32ArrayGPU, Date32ArrayGPU], [Date32ArrayGPU, Int32ArrayGPU]]);
-dyn_pair!(/// Subtract a scalar from each element in the array
+dyn_pair!(/// column - one-element column
           sub_scalar_dyn, sub_scalar_op_dyn, sub_scalar_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, Date32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU],
           mixed: [[Int32ArrayGPU, Date32ArrayGPU], [Date32ArrayGPU, Int32ArrayGPU]]);
-dyn_pair!(/// Multiply a scalar to each element in the array
+dyn_pair!(/// column * one-element column
           mul_scalar_dyn, mul_scalar_op_dyn, mul_scalar_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, Date32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU],
           mixed: [[Int32ArrayGPU, Date32ArrayGPU], [Date32ArrayGPU, Int32ArrayGPU]]);
-dyn_pair!(/// Divide each element in the array by scalar
+dyn_pair!(/// column / one-element column
           div_scalar_dyn, div_scalar_op_dyn, div_scalar_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, Date32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU],
           mixed: [[Int32ArrayGPU, Date32ArrayGPU], [Date32ArrayGPU, Int32ArrayGPU]]);
-dyn_pair!(/// Find remainder of each element in the array by scalar
+dyn_pair!(/// column % one-element column
           rem_scalar_dyn, rem_scalar_op_dyn, rem_scalar_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, Date32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU],
           mixed: [[Int32ArrayGPU, Date32ArrayGPU], [Date32ArrayGPU, Int32ArrayGPU]]);
-dyn_pair!(/// Compute x + y for each pair (x, y) in zip(lhs, rhs)
+dyn_pair!(/// x + y, row by row over both columns
           add_array_dyn, add_array_op_dyn, add_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, Date32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU],
           mixed: [[Int32ArrayGPU, Date32ArrayGPU], [Date32ArrayGPU, Int32ArrayGPU]]);
-dyn_pair!(/// Compute x - y for each pair (x, y) in zip(lhs, rhs)
+dyn_pair!(/// x - y, row by row over both columns
           sub_array_dyn, sub_array_op_dyn, sub_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU], mixed: []);
-dyn_pair!(/// Compute x * y for each pair (x, y) in zip(lhs, rhs)
+dyn_pair!(/// x * y, row by row over both columns
           mul_array_dyn, mul_array_op_dyn, mul_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU], mixed: []);
-dyn_pair!(/// Compute x / y for each pair (x, y) in zip(lhs, rhs)
+dyn_pair!(/// x / y, row by row over both columns
           div_array_dyn, div_array_op_dyn, div_op,
           same: [Float32ArrayGPU, Int32ArrayGPU, UInt32ArrayGPU, UInt16ArrayGPU, Int16ArrayGPU, Int8ArrayGPU, UInt8ArrayGPU], mixed: []);
 

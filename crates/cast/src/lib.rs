@@ -76,7 +76,7 @@ impl BitCast<Float32ArrayGPU> for UInt32ArrayGPU {
     }
 }
 
-/// Cast x as `T` for each x in array (cast/src/lib.rs:111-161)
+/// every row converted to the element type `T` (cast/src/lib.rs:111-161)
 pub fn cast_dyn(from: &ArrowArrayGPU, into: &ArrowType) -> ArrowArrayGPU {
     let mut pipeline = ArrowComputePipeline::new(from.get_gpu_device(), None);
     let result = cast_op_dyn(from, into, &mut pipeline);
@@ -108,7 +108,7 @@ pub fn cast_op_dyn(from: &ArrowArrayGPU, into: &ArrowType, pipeline: &mut ArrowC
     }
 }
 
-/// Reinterpret x as `T` for each x in array (cast/src/lib.rs:163-192)
+/// the same bits of every row read as `T` (cast/src/lib.rs:163-192)
 pub fn bitcast_dyn(from: &ArrowArrayGPU, into: &ArrowType) -> ArrowArrayGPU {
     let mut pipeline = ArrowComputePipeline::new(from.get_gpu_device(), None);
     let result = bitcast_op_dyn(from, into, &mut pipeline);

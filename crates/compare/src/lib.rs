@@ -144,18 +144,18 @@ macro_rules! dyn_same_type {
     )*};
 }
 dyn_same_type!(
-    [/// Construct bool array from computing x > y for each pair (x, y)
+    [/// row-wise predicate x > y into a BooleanArrayGPU
      gt_dyn, gt_op_dyn, gt_op],
-    [/// Construct bool array from computing x >= y for each pair (x, y)
+    [/// row-wise predicate x >= y into a BooleanArrayGPU
      gteq_dyn, gteq_op_dyn, gteq_op],
-    [/// Construct bool array from computing x < y for each pair (x, y)
+    [/// row-wise predicate x < y into a BooleanArrayGPU
      lt_dyn, lt_op_dyn, lt_op],
-    [/// Construct bool array from computing x <= y for each pair (x, y)
+    [/// row-wise predicate x <= y into a BooleanArrayGPU
      lteq_dyn, lteq_op_dyn, lteq_op],
-    [/// Construct bool array from computing x == y for each pair (x, y)
+    [/// row-wise predicate x == y into a BooleanArrayGPU
      eq_dyn, eq_op_dyn, eq_op],
-    [/// Compute max(x, y) for each pair (x, y) in zip(lhs, rhs)
+    [/// max(x, y), row by row over both columns
      max_dyn, max_op_dyn, max_op],
-    [/// Compute min(x, y) for each pair (x, y) in zip(lhs, rhs)
+    [/// min(x, y), row by row over both columns
      min_dyn, min_op_dyn, min_op]
 );

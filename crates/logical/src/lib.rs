@@ -208,11 +208,11 @@ macro_rules! dyn_binary {
     )*};
 }
 dyn_binary!(
-    [/// Compute x & y for each pair (x, y)
+    [/// x & y, row by row over both columns
      bitwise_and_dyn, bitwise_and_op_dyn, bitwise_and_op],
-    [/// Compute x | y for each pair (x, y)
+    [/// x | y, row by row over both columns
      bitwise_or_dyn, bitwise_or_op_dyn, bitwise_or_op],
-    [/// Compute x ^ y for each pair (x, y)
+    [/// x ^ y, row by row over both columns
      bitwise_xor_dyn, bitwise_xor_op_dyn, bitwise_xor_op]
 );
 
@@ -241,9 +241,9 @@ macro_rules! dyn_shift {
     )*};
 }
 dyn_shift!(
-    [/// Compute x << y for each pair (x, y)
+    [/// x << y, row by row over both columns
      bitwise_shl_dyn, bitwise_shl_op_dyn, bitwise_shl_op],
-    [/// Compute x >> y for each pair (x, y)
+    [/// x >> y, row by row over both columns
      bitwise_shr_dyn, bitwise_shr_op_dyn, bitwise_shr_op]
 );
 

@@ -153,19 +153,19 @@ macro_rules! dyn_unary {
     )*};
 }
 dyn_unary!(
-    [/// Compute abs(x) for each x in array
+    [/// abs(x) of every row
      abs_dyn, abs_op_dyn, abs_op, Float32ArrayGPU, Int32ArrayGPU],
-    [/// Compute square_root(x) for each x in array
+    [/// square_root(x) of every row
      sqrt_dyn, sqrt_op_dyn, sqrt_op, Float32ArrayGPU],
-    [/// Compute cube_root(x) for each x in array
+    [/// cube_root(x) of every row
      cbrt_dyn, cbrt_op_dyn, cbrt_op, Float32ArrayGPU],
-    [/// Compute e^x for each x in array
+    [/// e^x of every row
      exp_dyn, exp_op_dyn, exp_op, Float32ArrayGPU],
-    [/// Compute 2^x for each x in array
+    [/// 2^x of every row
      exp2_dyn, exp2_op_dyn, exp2_op, Float32ArrayGPU],
-    [/// Compute log(x) for each x in array
+    [/// log(x) of every row
      log_dyn, log_op_dyn, log_op, Float32ArrayGPU],
-    [/// Compute log_to_base_2(x) for each x in array
+    [/// log_to_base_2(x) of every row
      log2_dyn, log2_op_dyn, log2_op, Float32ArrayGPU]
 );
 

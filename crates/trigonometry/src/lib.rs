@@ -102,12 +102,12 @@ macro_rules! dyn_unary {
     )*};
 }
 dyn_unary!(
-    [/// Compute sinh(x) for each x in array
+    [/// sinh(x) of every row
      sinh_dyn, sinh_op_dyn, sinh_op, Float32ArrayGPU, UInt16ArrayGPU, UInt8ArrayGPU, Int16ArrayGPU, Int8ArrayGPU],
-    [/// Compute cos(x) for each x in array
+    [/// cos(x) of every row
      cos_dyn, cos_op_dyn, cos_op, Float32ArrayGPU, UInt16ArrayGPU, UInt8ArrayGPU, Int16ArrayGPU, Int8ArrayGPU],
-    [/// Compute sin(x) for each x in array
+    [/// sin(x) of every row
      sin_dyn, sin_op_dyn, sin_op, Float32ArrayGPU, UInt16ArrayGPU, UInt8ArrayGPU, Int16ArrayGPU, Int8ArrayGPU],
-    [/// Compute acos(x) for each x in array
+    [/// acos(x) of every row
      acos_dyn, acos_op_dyn, acos_op, Float32ArrayGPU]
 );
