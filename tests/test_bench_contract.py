@@ -68,3 +68,17 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert abs(line["value"] - 55 * 65536 / (line["ms_per_step"] * 1e-3)) / line["value"] < 0.01
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """the driver launches the reference arm like ours: under torchrun at N > 1 only rank 0 works and prints"""
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29593", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--rows", "65536", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, cwd=ROOT,
+                         timeout=280)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["config"] == bench.config_dict(65536)
